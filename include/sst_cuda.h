@@ -1,0 +1,113 @@
+/*
+ * sst_cuda.h -- C ABI of libsst_cuda.so, the B200 (sm_100a) provider for the FftService and ArrayKernel
+ * service-provider interfaces of carsomyr/Shared.
+ *
+ * This is the drop-in boundary: the JNI glue (shared_b200/csrc/jni_glue.cpp), the Python host mirror
+ * (shared_b200/) and bench.py all bind exactly these entry points. Plain pointers and sizes only.
+ * Citations are relative to /root/reference.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; sstc_last_error() then holds the message
+ *     that the JNI glue raises as java.lang.RuntimeException (native/src/shared/Common.cpp:173-178 does the
+ *     same for the reference's C++ exceptions). No C++ exception crosses this ABI.
+ *   - HOST tier (`sstc_<op>`): pointers are host memory, exactly the arrays the Java SPI passes; the library
+ *     stages them through HBM (H2D, kernels, D2H) and returns when the result is in the caller's array.
+ *   - DEVICE tier (`sstc_<op>_dev`, plans): pointers are device memory on the current device and the call
+ *     is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *   - complex data is interleaved re/im float64, row-major, as in org.shared.array.ComplexArray.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef SST_CUDA_H
+#define SST_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSTC_ABI_VERSION 1
+
+/* ---- library / device ------------------------------------------------------------------------------- */
+
+/* Replaces JNI_OnLoad's provider registration (native/src/shared_common/Library.cpp:55-77): selects the
+ * CUDA device the calling thread will use and checks it is an sm_100 part. */
+int sstc_init(int device);
+int sstc_shutdown(void);
+/* Thread-local message of the last failed call ("" if none). */
+const char *sstc_last_error(void);
+int sstc_abi_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t sstc_launch_count(void);
+
+/* Device-tier memory helpers (cudaMalloc / cudaFree / cudaMemcpy on the current device). */
+int sstc_malloc(void **dptr, int64_t bytes);
+int sstc_free(void *dptr);
+int sstc_host_alloc(void **hptr, int64_t bytes); /* pinned host memory */
+int sstc_host_free(void *hptr);
+int sstc_h2d(void *dst, const void *src, int64_t bytes, void *stream);
+int sstc_d2h(void *dst, const void *src, int64_t bytes, void *stream);
+int sstc_d2d(void *dst, const void *src, int64_t bytes, void *stream);
+int sstc_memset(void *dst, int value, int64_t bytes, void *stream);
+int sstc_stream_sync(void *stream);
+
+/* ---- FftService ------------------------------------------------------------------------------------ */
+
+/* Transform kinds; values are those of org.sharedx.fftw.Plan (src_extensions/org/sharedx/fftw/Plan.java:73-88). */
+#define SSTC_FFT_R2C 0      /* FftService.rfft  (src/org/shared/fft/FftService.java:50)  */
+#define SSTC_FFT_C2R 1      /* FftService.rifft (FftService.java:62), scaled by 1/N     */
+#define SSTC_FFT_FORWARD 2  /* FftService.fft   (FftService.java:74), e^{-2 pi i jk/n}, unscaled */
+#define SSTC_FFT_BACKWARD 3 /* FftService.ifft  (FftService.java:86), scaled by 1/N     */
+
+/* Expected array lengths in doubles for a transform; the rules of Plan::getTransformParameters
+ * (native/src/sharedx/Plan.cpp:230-320). `dims` are the logical dims (real dims for R2C/C2R, no trailing 2). */
+int sstc_fft_lengths(int kind, int rank, const int32_t *dims, int64_t *in_len, int64_t *out_len);
+
+/* HOST tier. Replaces Java_org_sharedx_fftw_Plan_transform (native/src/sharedx/BindingsX.cpp:26-29,
+ * Plan.cpp:44-99) and JavaFftService.{fft,ifft,rfft,rifft} (src/org/shared/fft/JavaFftService.java:53-94).
+ * `in` is preserved. Length mismatch fails with "Input and/or output arrays do not have expected sizes". */
+int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t in_len, double *out,
+        int64_t out_len);
+
+/* DEVICE tier. A plan replaces the fftw_plan held by org.sharedx.fftw.Plan (Plan.cpp:101-141 create,
+ * :143-175 destroy); creation is serialised internally, execution is re-entrant per stream. */
+typedef struct sstc_fft_plan_s *sstc_fft_plan;
+int sstc_fft_plan_create(sstc_fft_plan *plan, int kind, int rank, const int32_t *dims);
+int sstc_fft_plan_execute(sstc_fft_plan plan, const double *d_in, double *d_out, void *stream);
+int sstc_fft_plan_destroy(sstc_fft_plan plan);
+/* Bytes of device workspace the plan owns, and the number of kernel launches one execute issues. */
+int64_t sstc_fft_plan_workspace(sstc_fft_plan plan);
+int sstc_fft_plan_launches(sstc_fft_plan plan);
+/* Plan tunables (FftService.setHint analogue; FftwService.java:93-143). Known names: "chunk_planes"
+ * (planes per L2-resident chunk of the fused last-two-axes schedule; 0 = one launch per axis). Unknown
+ * names fail with "Unknown hint" (JavaFftService.java:96-104). */
+int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value);
+
+/* One axis pass of a row-major complex array viewed as (outer, len, inner): the building block the
+ * slab-sharded multi-GPU transform (shared_b200/sharded.py) composes around its exchange step.
+ * `inverse` selects e^{+2 pi i jk/n}; every output is multiplied by `scale`. In place when d_in == d_out. */
+int sstc_fft_axis_dev(const double *d_in, double *d_out, int64_t outer, int32_t len, int64_t inner, int inverse,
+        double scale, void *stream);
+
+/* The same pass with blocked addressing on either side. The axis is cut into n equal blocks of len/n points;
+ * point k of plane o, column i lives at blocks[k / (len/n)] + (o*(len/n) + k % (len/n))*pitch + i (complex
+ * elements; pitch 0 = inner, i.e. each block is a dense (outer, len/n, inner) array; n = 1 with pitch 0 is
+ * the plain layout). `d_*_blocks` are HOST arrays of device pointers, n <= 8. Pointing the output blocks at
+ * the peers' receive buffers (P2P-mapped) turns the pass into "FFT + slab transpose over NVLink" in one
+ * kernel; the input side reads an axis that an all-to-all delivered as one block per source rank. */
+int sstc_fft_axis_blocked_dev(void *const *d_in_blocks, int n_in, int64_t in_pitch, void *const *d_out_blocks,
+        int n_out, int64_t out_pitch, int64_t outer, int32_t len, int64_t inner, int inverse, double scale,
+        void *stream);
+
+/* Cross-process device-memory sharing for the one-process-per-GPU layout (cudaIpc*): export a 64-byte
+ * handle for a buffer from sstc_malloc, open a peer's handle, close it. */
+#define SSTC_IPC_HANDLE_BYTES 64
+int sstc_ipc_export(void *dptr, unsigned char handle[SSTC_IPC_HANDLE_BYTES]);
+int sstc_ipc_open(const unsigned char handle[SSTC_IPC_HANDLE_BYTES], void **dptr);
+int sstc_ipc_close(void *dptr);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SST_CUDA_H */

@@ -1,0 +1,414 @@
+// fft_kernels.cuh -- sm_100a device code for one axis pass of an n-D complex128 FFT.
+//
+// A row-major complex array is viewed as (outer, L, inner); one pass transforms every length-L line
+// (o, :, i). The reference does the same work one line at a time on the CPU
+// (src/org/shared/fft/FftOps.java:65-84 per-dimension loop, :173-248 butterflies); here a CTA owns a tile of
+// C lines and runs a Stockham autosort FFT on it:
+//
+//   * each thread keeps 8 points of one line in registers; thread t of a line owns points t + m*(L/8),
+//     m = 0..7, in EVERY stage, so the first stage is fed straight from HBM and the last stage stores
+//     straight to HBM -- both as coalesced 16-byte (double2) accesses;
+//   * stages are radix 8 (then one radix 4 or 2 if log2 L is not a multiple of 3), computed in registers;
+//     between stages the tile is exchanged through shared memory (one write + one read of 16 B / point);
+//   * CONTIG tiles (inner == 1) hold C whole lines, STRIDED tiles (inner > 1) hold C adjacent columns of
+//     the (L x inner) plane so that every row segment of the tile is C*16 contiguous bytes in HBM;
+//   * the inverse transform reuses the forward butterflies through the swap identity
+//     ifft(x) = swap(fft(swap(x))), swap(a+ib) = b+ia, applied on load and store;
+//   * r2c / c2r (last axis only) are load/store variants of the same kernel: r2c promotes a real line and
+//     keeps bins [0, L/2]; c2r rebuilds the Hermitian line x[L-k] = conj(x[k]) on load and stores Re.
+//
+// HBM traffic per pass is the algorithmic minimum for an axis-separable schedule: 16 B read + 16 B written
+// per point.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sstc {
+
+enum FftMode : int { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
+
+struct FftPassArgs {
+    const double2 *in;   // c2c / c2r: complex input; r2c: reinterpret as const double*
+    double2 *out;        // c2c / r2c: complex output; c2r: reinterpret as double*
+    const double2 *tw;   // tw[m] = exp(-2 pi i m / L), m in [0, L)
+    int64_t outer;       // number of (L x inner) planes
+    int64_t inner;       // stride between consecutive points of a line, in elements
+    int64_t in_plane;    // elements between consecutive planes of the input (== L*inner unless sub-viewed)
+    int64_t out_plane;
+    double scale;        // applied on store
+    int mode;            // FftMode
+    int inverse;         // 0: e^{-i..}, 1: e^{+i..}
+    // Blocked addressing (STRIDED c2c only; ksplit == 0 = off). The axis is cut into blocks of `ksplit`
+    // points; point k of plane o, column i lives at blk[k / ksplit] + (o*ksplit + k % ksplit)*pitch + i.
+    // On the store side, with blk[] pointing into the peers' receive buffers, this IS the slab transpose of
+    // the multi-GPU transform (pack, send and unpack fused into the pass's store); on the load side it reads
+    // an axis that an all-to-all delivered as one block per source rank.
+    int ksplit;
+    int in_ksplit;
+    int64_t blk_pitch;
+    int64_t in_blk_pitch;
+    double2 *blk[8];
+    const double2 *in_blk[8];
+};
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 w) {
+    return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+}
+// a * (-i)
+__device__ __forceinline__ double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
+
+// In-register DFTs over v[0], v[S], v[2S], ... (forward sign), outputs in natural order at the same slots.
+template <int S>
+__device__ __forceinline__ void dft2(double2 *v) {
+    double2 a = v[0], b = v[S];
+    v[0] = cadd(a, b);
+    v[S] = csub(a, b);
+}
+
+template <int S>
+__device__ __forceinline__ void dft4(double2 *v) {
+    double2 c0 = cadd(v[0], v[2 * S]), c1 = csub(v[0], v[2 * S]);
+    double2 c2 = cadd(v[S], v[3 * S]), c3 = cmul_mi(csub(v[S], v[3 * S]));
+    v[0] = cadd(c0, c2);
+    v[S] = cadd(c1, c3);
+    v[2 * S] = csub(c0, c2);
+    v[3 * S] = csub(c1, c3);
+}
+
+__device__ __forceinline__ void dft8(double2 *v) {
+    const double h = 0.70710678118654752440;
+    double2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    double2 a1 = cadd(v[1], v[5]), d5 = csub(v[1], v[5]);
+    double2 a2 = cadd(v[2], v[6]), a6 = cmul_mi(csub(v[2], v[6]));
+    double2 a3 = cadd(v[3], v[7]), d7 = csub(v[3], v[7]);
+    // d5 * (1 - i)/sqrt2 ; d7 * (-1 - i)/sqrt2
+    double2 a5 = make_double2((d5.x + d5.y) * h, (d5.y - d5.x) * h);
+    double2 a7 = make_double2((d7.y - d7.x) * h, -(d7.x + d7.y) * h);
+    // even outputs: DFT4(a0,a1,a2,a3); odd outputs: DFT4(a4,a5,a6,a7)
+    double2 c0 = cadd(a0, a2), c1 = csub(a0, a2), c2 = cadd(a1, a3), c3 = cmul_mi(csub(a1, a3));
+    v[0] = cadd(c0, c2);
+    v[2] = cadd(c1, c3);
+    v[4] = csub(c0, c2);
+    v[6] = csub(c1, c3);
+    double2 e0 = cadd(a4, a6), e1 = csub(a4, a6), e2 = cadd(a5, a7), e3 = cmul_mi(csub(a5, a7));
+    v[1] = cadd(e0, e2);
+    v[3] = cadd(e1, e3);
+    v[5] = csub(e0, e2);
+    v[7] = csub(e1, e3);
+}
+
+template <int R, int B>
+__device__ __forceinline__ void dftR(double2 *v) {
+    if (R == 8) {
+        dft8(v);
+    } else if (R == 4) {
+        dft4<B>(v);
+    } else {
+        dft2<B>(v);
+    }
+}
+
+__host__ __device__ constexpr int fft_pad(int pos) { return pos + (pos >> 3); }
+
+// Tile geometry shared by host (launch configuration) and device.
+template <int L, int C, bool STRIDED>
+struct Pow2Tile {
+    static constexpr int T = L / 8;                 // threads per line
+    static constexpr int THREADS = C * T;
+    static constexpr bool PADDED = !STRIDED || (C < 8);
+    static constexpr int LINE = PADDED ? fft_pad(L) : L;  // smem elements per line
+    static constexpr int SMEM_BYTES = (L > 8) ? LINE * C * 16 : 0;
+};
+
+// One Stockham stage with Ns = NS already-combined points, followed (if not last) by the smem exchange and
+// the remaining stages.
+template <int L, int C, bool STRIDED, int NS>
+struct Pow2Stages {
+    static constexpr int REM = L / NS;
+    static constexpr int R = REM >= 8 ? 8 : REM;
+    static constexpr int B = 8 / R;
+    static constexpr int T = L / 8;
+    using Tile = Pow2Tile<L, C, STRIDED>;
+
+    __device__ __forceinline__ static int sidx(int pos, int c) {
+        int p = Tile::PADDED ? fft_pad(pos) : pos;
+        return STRIDED ? p * C + c : c * Tile::LINE + p;
+    }
+
+    __device__ __forceinline__ static void run(double2 (&v)[8], int t, int c, double2 *sm,
+            const double2 *__restrict__ tw) {
+        if (NS > 1) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                int k = (t + b * T) & (NS - 1);
+#pragma unroll
+                for (int r = 1; r < R; r++) {
+                    double2 w = __ldg(&tw[r * k * (L / (NS * R))]);
+                    v[b + r * B] = cmul(v[b + r * B], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            dftR<R, B>(&v[b]);
+        }
+        if (NS * R < L) {
+            if (NS > 1) {
+                __syncthreads();  // everyone has finished reading the previous exchange
+            }
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                int j = t + b * T;
+                int k = j & (NS - 1);
+                int j0 = (j - k) * R + k;
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    sm[sidx(j0 + q * NS, c)] = v[b + q * B];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                v[m] = sm[sidx(t + m * T, c)];
+            }
+            Pow2Stages<L, C, STRIDED, (NS * R < L ? NS * R : L)>::run(v, t, c, sm, tw);
+        }
+    }
+};
+
+template <int L, int C, bool STRIDED>
+struct Pow2Stages<L, C, STRIDED, L> {
+    __device__ __forceinline__ static void run(double2 (&)[8], int, int, double2 *, const double2 *) {}
+};
+
+template <int L, int C, bool STRIDED>
+__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS)
+fft_pow2_kernel(const FftPassArgs a) {
+    using Tile = Pow2Tile<L, C, STRIDED>;
+    constexpr int T = Tile::T;
+    extern __shared__ double2 sm[];
+
+    const int tid = threadIdx.x;
+    int c, t;
+    if (STRIDED) {
+        c = tid % C;
+        t = tid / C;
+    } else {
+        t = tid % T;
+        c = tid / T;
+    }
+
+    // Locate the tile. STRIDED: blockIdx.x -> (plane o, column tile); CONTIG: blockIdx.x -> C lines.
+    bool active;
+    int64_t in_base, out_base, estride;
+    int64_t line = 0;  // CONTIG line number (for r2c / c2r addressing)
+    int64_t o = 0, i = 0;
+    if (STRIDED) {
+        const int64_t tiles_per_plane = (a.inner + C - 1) / C;
+        o = blockIdx.x / tiles_per_plane;
+        i = (blockIdx.x - o * tiles_per_plane) * C + c;
+        active = i < a.inner;
+        in_base = o * a.in_plane + i;
+        out_base = o * a.out_plane + i;
+        estride = a.inner;
+    } else {
+        line = (int64_t) blockIdx.x * C + c;
+        active = line < a.outer;
+        in_base = line * a.in_plane;
+        out_base = line * a.out_plane;
+        estride = 1;
+    }
+
+    double2 v[8];
+    if (active) {
+        if (STRIDED && a.in_ksplit > 0) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int p = t + m * T;
+                const int q = p / a.in_ksplit;
+                const int pk = p - q * a.in_ksplit;
+                v[m] = a.in_blk[q][(o * a.in_ksplit + pk) * a.in_blk_pitch + i];
+            }
+        } else if (a.mode == MODE_C2C) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                v[m] = a.in[in_base + (int64_t) (t + m * T) * estride];
+            }
+        } else if (a.mode == MODE_R2C) {
+            const double *rin = reinterpret_cast<const double *>(a.in) + line * L;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                v[m] = make_double2(rin[t + m * T], 0.0);
+            }
+        } else {  // MODE_C2R: half-complex line of L/2+1 bins
+            const double2 *hin = a.in + line * (L / 2 + 1);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                int p = t + m * T;
+                if (p <= L / 2) {
+                    v[m] = hin[p];
+                } else {
+                    double2 z = hin[L - p];
+                    v[m] = make_double2(z.x, -z.y);
+                }
+            }
+        }
+        if (a.inverse) {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                v[m] = make_double2(v[m].y, v[m].x);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            v[m] = make_double2(0.0, 0.0);
+        }
+    }
+
+    Pow2Stages<L, C, STRIDED, 1>::run(v, t, c, sm, a.tw);
+
+    if (!active) {
+        return;
+    }
+    const double s = a.scale;
+    if (STRIDED && a.ksplit > 0) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+            const int p = t + m * T;
+            const int q = p / a.ksplit;
+            const int pk = p - q * a.ksplit;
+            a.blk[q][(o * a.ksplit + pk) * a.blk_pitch + i] = z;
+        }
+    } else if (a.mode == MODE_C2C) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+            a.out[out_base + (int64_t) (t + m * T) * estride] = z;
+        }
+    } else if (a.mode == MODE_R2C) {
+        double2 *hout = a.out + line * (L / 2 + 1);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            int p = t + m * T;
+            if (p <= L / 2) {
+                hout[p] = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+            }
+        }
+    } else {
+        double *rout = reinterpret_cast<double *>(a.out) + line * L;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            rout[t + m * T] = (a.inverse ? v[m].y : v[m].x) * s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Any-length fallback kernel (still on the GPU; there is no CPU path): one line per CTA, Stockham autosort
+// over the prime factors of L with O(p) work per output, ping-ponging between two shared-memory buffers.
+// Exact DFT for every L that fits (2 * 16 * L bytes of shared memory); used for the non-power-of-two
+// lengths the reference's own tests exercise (3, 5, 6, 7, 27: ArrayFftTest.java:61-224) and for L < 8.
+// ---------------------------------------------------------------------------------------------------------
+#define SSTC_FFT_MAX_FACTORS 32
+
+struct FftGenericArgs {
+    FftPassArgs p;
+    int L;
+    int nfactors;
+    int factors[SSTC_FFT_MAX_FACTORS];
+};
+
+__global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g) {
+    extern __shared__ double2 sm[];
+    const FftPassArgs &a = g.p;
+    const int L = g.L;
+    double2 *cur = sm, *nxt = sm + L;
+
+    // blockIdx -> line (o, i)
+    const int64_t o = blockIdx.x / a.inner;
+    const int64_t i = blockIdx.x - o * a.inner;
+    const int64_t line = blockIdx.x;  // r2c / c2r are launched with inner == 1
+    const int half = L / 2 + 1;
+
+    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+        double2 z;
+        if (a.in_ksplit > 0) {
+            const int q = p / a.in_ksplit;
+            const int pk = p - q * a.in_ksplit;
+            z = a.in_blk[q][(o * a.in_ksplit + pk) * a.in_blk_pitch + i];
+        } else if (a.mode == MODE_C2C) {
+            z = a.in[o * a.in_plane + (int64_t) p * a.inner + i];
+        } else if (a.mode == MODE_R2C) {
+            z = make_double2(reinterpret_cast<const double *>(a.in)[line * L + p], 0.0);
+        } else {
+            if (p < half) {
+                z = a.in[line * half + p];
+            } else {
+                z = a.in[line * half + (L - p)];
+                z.y = -z.y;
+            }
+        }
+        cur[p] = a.inverse ? make_double2(z.y, z.x) : z;
+    }
+    __syncthreads();
+
+    int ns = 1;
+    for (int f = 0; f < g.nfactors; f++) {
+        const int p = g.factors[f];
+        const int lp = L / p;        // input stride between the p legs of a butterfly
+        const int m = ns * p;
+        const int tstep = L / m;     // twiddle exponent unit for w_{ns*p}
+        for (int idx = threadIdx.x; idx < L; idx += blockDim.x) {
+            const int k = idx % ns;
+            const int q = (idx / ns) % p;
+            const int jhi = idx / m;
+            const int j = jhi * ns + k;
+            // exponent advanced per leg r: r * (k*L/(ns*p) + q*L/p)  (mod L)
+            const int step = (int) (((int64_t) k * tstep + (int64_t) q * lp) % L);
+            int e = 0;
+            double2 acc = cur[j];
+            for (int r = 1; r < p; r++) {
+                e += step;
+                if (e >= L) {
+                    e -= L;
+                }
+                const double2 w = __ldg(&a.tw[e]);
+                const double2 x = cur[j + r * lp];
+                acc.x += x.x * w.x - x.y * w.y;
+                acc.y += x.x * w.y + x.y * w.x;
+            }
+            nxt[idx] = acc;
+        }
+        __syncthreads();
+        double2 *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+        ns = m;
+    }
+
+    const double s = a.scale;
+    for (int p = threadIdx.x; p < L; p += blockDim.x) {
+        double2 z = cur[p];
+        z = a.inverse ? make_double2(z.y * s, z.x * s) : make_double2(z.x * s, z.y * s);
+        if (a.ksplit > 0) {
+            const int q = p / a.ksplit;
+            const int pk = p - q * a.ksplit;
+            a.blk[q][(o * a.ksplit + pk) * a.blk_pitch + i] = z;
+        } else if (a.mode == MODE_C2C) {
+            a.out[o * a.out_plane + (int64_t) p * a.inner + i] = z;
+        } else if (a.mode == MODE_R2C) {
+            if (p < half) {
+                a.out[line * half + p] = z;
+            }
+        } else {
+            reinterpret_cast<double *>(a.out)[line * L + p] = z.x;
+        }
+    }
+}
+
+}  // namespace sstc

@@ -1,0 +1,543 @@
+// fft_plan.cu -- FftService half of the C ABI: plans, twiddle tables, axis-pass dispatch, host tier.
+//
+// Replaces (paths relative to /root/reference):
+//   src/org/shared/fft/JavaFftService.java:53-94 + FftOps.java:55-106   (pure-Java provider)
+//   native/src/sharedx/Plan.cpp:44-141,230-437                            (FFTW-backed provider)
+// Schedule for dims (d0..d_{r-1}), row-major: the last axis first (out of place, in -> out), then every
+// other axis in place on `out`; the inverse applies 1/N in the last pass. The reference's per-dimension
+// loop (FftOps.java:65-84) visits the same axes, rotating the layout each time instead.
+#include <math.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft_kernels.cuh"
+#include "sstc_internal.h"
+
+namespace sstc {
+
+// ---- twiddle tables -----------------------------------------------------------------------------------
+
+static std::mutex g_tw_mutex;
+static std::map<std::pair<int, int>, double2 *> g_tw_cache;  // (device, L) -> table
+
+// tw[m] = exp(-2 pi i m / L), evaluated in long double then rounded (FftOps.java:155-168 uses double
+// cos/sin of a double phase; this is at least as accurate).
+static const double2 *twiddles_for(int L) {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto key = std::make_pair(dev, L);
+    auto it = g_tw_cache.find(key);
+    if (it != g_tw_cache.end()) {
+        return it->second;
+    }
+    std::vector<double2> host((size_t) L);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int m = 0; m < L; m++) {
+        // octant symmetry keeps exact values (0, +-1, +-sqrt(1/2)) exact
+        long double ang = two_pi * (long double) m / (long double) L;
+        host[(size_t) m] = make_double2((double) cosl(ang), (double) -sinl(ang));
+    }
+    if (L % 4 == 0) {
+        host[(size_t) (L / 4)] = make_double2(0.0, -1.0);
+        host[(size_t) (L / 2)] = make_double2(-1.0, 0.0);
+        host[(size_t) (3 * (L / 4))] = make_double2(0.0, 1.0);
+    } else if (L % 2 == 0) {
+        host[(size_t) (L / 2)] = make_double2(-1.0, 0.0);
+    }
+    double2 *d = nullptr;
+    SSTC_CUDA(cudaMalloc(&d, sizeof(double2) * (size_t) L));
+    SSTC_CUDA(cudaMemcpy(d, host.data(), sizeof(double2) * (size_t) L, cudaMemcpyHostToDevice));
+    g_tw_cache[key] = d;
+    return d;
+}
+
+// ---- axis-pass dispatch ------------------------------------------------------------------------------
+
+constexpr int strided_cols(int L) { return L <= 64 ? 32 : L <= 256 ? 16 : L <= 512 ? 8 : L <= 1024 ? 4 : 2; }
+constexpr int contig_lines(int L) { return (256 / (L / 8)) < 1 ? 1 : (256 / (L / 8)) > 64 ? 64 : (256 / (L / 8)); }
+
+static const int64_t kMaxGrid = 2147483647LL;
+static const int kGenericMaxL = 7168;  // two ping-pong buffers of 16*L bytes within 227 KB of shared memory
+
+template <int L, int C, bool STRIDED>
+static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream) {
+    using Tile = Pow2Tile<L, C, STRIDED>;
+    static std::once_flag once[16];  // per device
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    if (Tile::SMEM_BYTES > 48 * 1024) {
+        std::call_once(once[dev & 15], [] {
+            SSTC_CUDA(cudaFuncSetAttribute(fft_pow2_kernel<L, C, STRIDED>,
+                    cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM_BYTES));
+        });
+    }
+    if (grid > kMaxGrid) {
+        throw std::runtime_error("FFT batch too large for one launch");
+    }
+    fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
+    check_launch("fft_pow2_kernel");
+}
+
+template <int L>
+static void launch_pow2_L(const FftPassArgs &a, bool strided, cudaStream_t stream) {
+    if (strided) {
+        constexpr int C = strided_cols(L);
+        int64_t tiles = (a.inner + C - 1) / C;
+        launch_pow2<L, C, true>(a, a.outer * tiles, stream);
+    } else {
+        constexpr int C = contig_lines(L);
+        launch_pow2<L, C, false>(a, (a.outer + C - 1) / C, stream);
+    }
+}
+
+static std::vector<int> prime_factors(int n) {
+    std::vector<int> f;
+    for (int p = 2; (int64_t) p * p <= n; p++) {
+        while (n % p == 0) {
+            f.push_back(p);
+            n /= p;
+        }
+    }
+    if (n > 1) {
+        f.push_back(n);
+    }
+    return f;
+}
+
+static void launch_generic(const FftPassArgs &a, int L, cudaStream_t stream) {
+    if (L > kGenericMaxL) {
+        throw std::runtime_error("FFT length " + std::to_string(L) + " is not supported by the CUDA provider");
+    }
+    FftGenericArgs g;
+    g.p = a;
+    g.L = L;
+    std::vector<int> f = prime_factors(L);
+    if ((int) f.size() > SSTC_FFT_MAX_FACTORS) {
+        throw std::runtime_error("FFT length has too many factors");
+    }
+    g.nfactors = (int) f.size();
+    for (size_t i = 0; i < f.size(); i++) {
+        g.factors[i] = f[i];
+    }
+    size_t smem = (size_t) 2 * 16 * (size_t) L;
+    static std::once_flag once[16];
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 15], [] {
+        SSTC_CUDA(cudaFuncSetAttribute(fft_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                2 * 16 * kGenericMaxL));
+    });
+    int64_t lines = a.outer * a.inner;
+    if (lines > kMaxGrid) {
+        throw std::runtime_error("FFT batch too large for one launch");
+    }
+    int threads = L >= 256 ? 256 : L >= 64 ? 64 : 32;
+    fft_generic_kernel<<<(unsigned) lines, threads, smem, stream>>>(g);
+    check_launch("fft_generic_kernel");
+}
+
+// Optional blocked addressing of one side of a pass (see FftPassArgs).
+struct Blocks {
+    int n = 0;
+    void *const *ptrs = nullptr;
+    int64_t pitch = 0;  // 0 = dense (== inner)
+};
+
+// One pass over axis `L` of (outer, L, inner). For MODE_R2C / MODE_C2R, inner must be 1 and outer counts lines.
+static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse,
+        double scale, cudaStream_t stream, const Blocks &bin = Blocks(), const Blocks &bout = Blocks()) {
+    if (outer <= 0 || inner <= 0 || L <= 0) {
+        return;
+    }
+    FftPassArgs a;
+    a.in = static_cast<const double2 *>(in);
+    a.out = static_cast<double2 *>(out);
+    a.tw = twiddles_for(L);
+    a.outer = outer;
+    a.inner = inner;
+    a.in_plane = (int64_t) L * inner;
+    a.out_plane = (int64_t) L * inner;
+    a.scale = scale;
+    a.mode = mode;
+    a.inverse = inverse;
+    a.ksplit = a.in_ksplit = 0;
+    a.blk_pitch = a.in_blk_pitch = inner;
+    for (int q = 0; q < 8; q++) {
+        a.blk[q] = nullptr;
+        a.in_blk[q] = nullptr;
+    }
+    if (bin.n > 0 || bout.n > 0) {
+        if (bin.n > 8 || bout.n > 8 || mode != MODE_C2C || (bin.n > 0 && (L % bin.n != 0 || !bin.ptrs)) ||
+                (bout.n > 0 && (L % bout.n != 0 || !bout.ptrs)) || bin.pitch < 0 || bout.pitch < 0 ||
+                (bin.pitch > 0 && bin.pitch < inner) || (bout.pitch > 0 && bout.pitch < inner)) {
+            throw std::runtime_error("Invalid block specification");
+        }
+        if (bin.n > 0) {
+            a.in_ksplit = L / bin.n;
+            a.in_blk_pitch = bin.pitch > 0 ? bin.pitch : inner;
+            for (int q = 0; q < bin.n; q++) {
+                a.in_blk[q] = static_cast<const double2 *>(bin.ptrs[q]);
+            }
+        }
+        if (bout.n > 0) {
+            a.ksplit = L / bout.n;
+            a.blk_pitch = bout.pitch > 0 ? bout.pitch : inner;
+            for (int q = 0; q < bout.n; q++) {
+                a.blk[q] = static_cast<double2 *>(bout.ptrs[q]);
+            }
+        }
+    }
+    // blocked addressing lives in the STRIDED kernels; inner == 1 is routed there as a 1-column plane
+    const bool strided = inner > 1 || bin.n > 0 || bout.n > 0;
+    switch (L) {
+    case 8: launch_pow2_L<8>(a, strided, stream); break;
+    case 16: launch_pow2_L<16>(a, strided, stream); break;
+    case 32: launch_pow2_L<32>(a, strided, stream); break;
+    case 64: launch_pow2_L<64>(a, strided, stream); break;
+    case 128: launch_pow2_L<128>(a, strided, stream); break;
+    case 256: launch_pow2_L<256>(a, strided, stream); break;
+    case 512: launch_pow2_L<512>(a, strided, stream); break;
+    case 1024: launch_pow2_L<1024>(a, strided, stream); break;
+    case 2048: launch_pow2_L<2048>(a, strided, stream); break;
+    case 4096: launch_pow2_L<4096>(a, strided, stream); break;
+    default: launch_generic(a, L, stream); break;
+    }
+}
+
+// ---- plans ----------------------------------------------------------------------------------------------
+
+struct Step {
+    int axis_len;
+    int64_t outer, inner;
+    int mode;
+    int src;  // 0 = caller's in, 1 = caller's out, 2 = workspace
+    int dst;  // 1 = caller's out, 2 = workspace
+    double scale;
+};
+
+}  // namespace sstc
+
+struct sstc_fft_plan_s {
+    int kind;
+    std::vector<int32_t> dims;
+    int64_t in_len, out_len;  // doubles
+    int inverse;
+    std::vector<sstc::Step> steps;
+    void *workspace = nullptr;
+    int64_t workspace_bytes = 0;
+    int64_t chunk_planes = 0;
+};
+
+namespace sstc {
+
+static void transform_lengths(int kind, int rank, const int32_t *dims, int64_t &in_len, int64_t &out_len) {
+    // Plan::getTransformParameters, native/src/sharedx/Plan.cpp:230-320 (64-bit instead of jint).
+    if (rank <= 0 || !dims) {
+        throw std::runtime_error("Rank must be greater than zero");
+    }
+    for (int i = 0; i < rank; i++) {
+        if (dims[i] <= 0) {
+            throw std::runtime_error("Invalid dimensions");
+        }
+    }
+    int64_t lead = 1;
+    for (int i = 0; i < rank - 1; i++) {
+        lead *= dims[i];
+    }
+    const int64_t last = dims[rank - 1];
+    switch (kind) {
+    case SSTC_FFT_R2C:
+        in_len = lead * last;
+        out_len = lead * 2 * (last / 2 + 1);
+        break;
+    case SSTC_FFT_C2R:
+        in_len = lead * 2 * (last / 2 + 1);
+        out_len = lead * last;
+        break;
+    case SSTC_FFT_FORWARD:
+    case SSTC_FFT_BACKWARD:
+        in_len = out_len = lead * 2 * last;
+        break;
+    default:
+        throw std::runtime_error("Transform type not recognized");
+    }
+}
+
+static void build_plan(sstc_fft_plan_s &p) {
+    const int rank = (int) p.dims.size();
+    int64_t n = 1;
+    for (int d : p.dims) {
+        n *= d;
+    }
+    p.inverse = (p.kind == SSTC_FFT_BACKWARD || p.kind == SSTC_FFT_C2R) ? 1 : 0;
+    const double inv_scale = p.inverse ? 1.0 / (double) n : 1.0;
+
+    if (p.kind == SSTC_FFT_FORWARD || p.kind == SSTC_FFT_BACKWARD) {
+        // last axis first (in -> out), then the others in place on out
+        int64_t inner = 1;
+        bool first = true;
+        for (int a = rank - 1; a >= 0; a--) {
+            const int L = p.dims[(size_t) a];
+            if (L > 1 || (a == 0 && first)) {
+                Step s{L, n / (L * inner), inner, MODE_C2C, first ? 0 : 1, 1, 1.0};
+                p.steps.push_back(s);
+                first = false;
+            }
+            inner *= L;
+        }
+        p.steps.back().scale = inv_scale;
+    } else if (p.kind == SSTC_FFT_R2C) {
+        const int last = p.dims[(size_t) rank - 1];
+        const int64_t half = last / 2 + 1;
+        p.steps.push_back(Step{last, n / last, 1, MODE_R2C, 0, 1, 1.0});
+        int64_t inner = half;
+        for (int a = rank - 2; a >= 0; a--) {
+            const int L = p.dims[(size_t) a];
+            if (L > 1) {
+                p.steps.push_back(Step{L, (n / last) * half / (L * inner), inner, MODE_C2C, 1, 1, 1.0});
+            }
+            inner *= L;
+        }
+    } else {  // C2R: leading axes on a workspace copy of the half-spectrum (the caller's `in` is preserved,
+              // as the reference does for FFTW's input-destroying c2r: Plan.cpp:428-437), then c2r -> out
+        const int last = p.dims[(size_t) rank - 1];
+        const int64_t half = last / 2 + 1;
+        const int64_t lines = n / last;
+        int64_t inner = half;
+        bool first = true;
+        for (int a = rank - 2; a >= 0; a--) {
+            const int L = p.dims[(size_t) a];
+            if (L > 1) {
+                p.steps.push_back(Step{L, lines * half / (L * inner), inner, MODE_C2C, first ? 0 : 2, 2, 1.0});
+                first = false;
+            }
+            inner *= L;
+        }
+        if (!first) {
+            p.workspace_bytes = lines * half * 16;
+        }
+        p.steps.push_back(Step{last, lines, 1, MODE_C2R, first ? 0 : 2, 1, inv_scale});
+    }
+    if (p.workspace_bytes > 0) {
+        SSTC_CUDA(cudaMalloc(&p.workspace, (size_t) p.workspace_bytes));
+    }
+    // Build every twiddle table now so execute() never allocates.
+    for (const Step &s : p.steps) {
+        twiddles_for(s.axis_len);
+    }
+}
+
+static void execute_plan(sstc_fft_plan_s &p, const double *d_in, double *d_out, cudaStream_t stream) {
+    if (!d_in || !d_out) {
+        throw std::runtime_error("Invalid arguments");
+    }
+    const size_t nsteps = p.steps.size();
+    // Fused schedule for the last two axes of a c2c transform: both passes touch one (d_{r-2} x d_{r-1})
+    // plane at a time, so running them back to back on a chunk of planes lets the second pass find the
+    // first pass's output in the 126 MB L2 instead of HBM.
+    const bool can_chunk = p.chunk_planes > 0 && nsteps >= 2 && p.steps[0].mode == MODE_C2C &&
+            p.steps[1].mode == MODE_C2C && p.steps[0].inner == 1 && p.steps[1].outer > 1;
+    size_t first_plain = 0;
+    if (can_chunk) {
+        const Step &s0 = p.steps[0], &s1 = p.steps[1];
+        const int64_t planes = s1.outer;
+        const int64_t plane_elems = (int64_t) s1.axis_len * s1.inner;  // complex elements per plane
+        const int64_t lines_per_plane = s1.axis_len;                    // s0 lines in one plane
+        const double2 *in = reinterpret_cast<const double2 *>(d_in);
+        double2 *out = reinterpret_cast<double2 *>(d_out);
+        for (int64_t p0 = 0; p0 < planes; p0 += p.chunk_planes) {
+            const int64_t np = (planes - p0 < p.chunk_planes) ? planes - p0 : p.chunk_planes;
+            launch_axis(in + p0 * plane_elems, out + p0 * plane_elems, np * lines_per_plane, s0.axis_len, 1,
+                    MODE_C2C, p.inverse, s0.scale, stream);
+            launch_axis(out + p0 * plane_elems, out + p0 * plane_elems, np, s1.axis_len, s1.inner, MODE_C2C,
+                    p.inverse, s1.scale, stream);
+        }
+        first_plain = 2;
+    }
+    for (size_t i = first_plain; i < nsteps; i++) {
+        const Step &s = p.steps[i];
+        const void *src = s.src == 0 ? (const void *) d_in : s.src == 1 ? (const void *) d_out : p.workspace;
+        void *dst = s.dst == 1 ? (void *) d_out : p.workspace;
+        launch_axis(src, dst, s.outer, s.axis_len, s.inner, s.mode, p.inverse, s.scale, stream);
+    }
+}
+
+static int plan_launches(const sstc_fft_plan_s &p) {
+    const size_t nsteps = p.steps.size();
+    const bool can_chunk = p.chunk_planes > 0 && nsteps >= 2 && p.steps[0].mode == MODE_C2C &&
+            p.steps[1].mode == MODE_C2C && p.steps[0].inner == 1 && p.steps[1].outer > 1;
+    if (!can_chunk) {
+        return (int) nsteps;
+    }
+    const int64_t planes = p.steps[1].outer;
+    const int64_t chunks = (planes + p.chunk_planes - 1) / p.chunk_planes;
+    return (int) (2 * chunks + (int64_t) nsteps - 2);
+}
+
+// Host-tier plan cache (FftwService keeps one too: FftwService.java:58-67,221-236). Guarded by one mutex;
+// host-tier calls are PCIe-bound, so serialising them costs nothing measurable.
+static std::mutex g_host_mutex;
+static std::map<std::vector<int32_t>, sstc_fft_plan_s *> g_host_plans;
+static Scratch g_host_in, g_host_out;
+
+}  // namespace sstc
+
+using namespace sstc;
+
+extern "C" {
+
+int sstc_fft_lengths(int kind, int rank, const int32_t *dims, int64_t *in_len, int64_t *out_len) {
+    return guarded([&] {
+        int64_t a = 0, b = 0;
+        transform_lengths(kind, rank, dims, a, b);
+        if (in_len) {
+            *in_len = a;
+        }
+        if (out_len) {
+            *out_len = b;
+        }
+    });
+}
+
+int sstc_fft_plan_create(sstc_fft_plan *plan, int kind, int rank, const int32_t *dims) {
+    return guarded([&] {
+        if (!plan) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        *plan = nullptr;
+        int64_t a = 0, b = 0;
+        transform_lengths(kind, rank, dims, a, b);
+        sstc_fft_plan_s *p = new sstc_fft_plan_s();
+        p->kind = kind;
+        p->dims.assign(dims, dims + rank);
+        p->in_len = a;
+        p->out_len = b;
+        try {
+            build_plan(*p);
+        } catch (...) {
+            if (p->workspace) {
+                cudaFree(p->workspace);
+            }
+            delete p;
+            throw;
+        }
+        *plan = p;
+    });
+}
+
+int sstc_fft_plan_execute(sstc_fft_plan plan, const double *d_in, double *d_out, void *stream) {
+    return guarded([&] {
+        if (!plan) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        execute_plan(*plan, d_in, d_out, as_stream(stream));
+    });
+}
+
+int sstc_fft_plan_destroy(sstc_fft_plan plan) {
+    return guarded([&] {
+        if (plan) {
+            if (plan->workspace) {
+                SSTC_CUDA(cudaFree(plan->workspace));
+            }
+            delete plan;
+        }
+    });
+}
+
+int64_t sstc_fft_plan_workspace(sstc_fft_plan plan) { return plan ? plan->workspace_bytes : 0; }
+
+int sstc_fft_plan_launches(sstc_fft_plan plan) { return plan ? plan_launches(*plan) : 0; }
+
+int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value) {
+    return guarded([&] {
+        if (!plan || !name) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (std::string(name) == "chunk_planes") {
+            if (value < 0) {
+                throw std::runtime_error("Invalid hint value");
+            }
+            plan->chunk_planes = value;
+        } else {
+            throw std::runtime_error("Unknown hint");
+        }
+    });
+}
+
+int sstc_fft_axis_dev(const double *d_in, double *d_out, int64_t outer, int32_t len, int64_t inner, int inverse,
+        double scale, void *stream) {
+    return guarded([&] {
+        if (!d_in || !d_out || outer < 0 || inner < 0 || len <= 0) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        launch_axis(d_in, d_out, outer, len, inner, MODE_C2C, inverse ? 1 : 0, scale, as_stream(stream));
+    });
+}
+
+int sstc_fft_axis_blocked_dev(void *const *d_in_blocks, int n_in, int64_t in_pitch, void *const *d_out_blocks,
+        int n_out, int64_t out_pitch, int64_t outer, int32_t len, int64_t inner, int inverse, double scale,
+        void *stream) {
+    return guarded([&] {
+        if (!d_in_blocks || !d_out_blocks || n_in <= 0 || n_out <= 0 || outer < 0 || inner < 0 || len <= 0) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        Blocks bin, bout;
+        bin.n = n_in;
+        bin.ptrs = d_in_blocks;
+        bin.pitch = in_pitch;
+        bout.n = n_out;
+        bout.ptrs = d_out_blocks;
+        bout.pitch = out_pitch;
+        launch_axis(nullptr, nullptr, outer, len, inner, MODE_C2C, inverse ? 1 : 0, scale, as_stream(stream), bin,
+                bout);
+    });
+}
+
+int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t in_len, double *out,
+        int64_t out_len) {
+    return guarded([&] {
+        if (!in || !out) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        int64_t a = 0, b = 0;
+        transform_lengths(kind, rank, dims, a, b);
+        if (in_len != a || out_len != b) {
+            // Plan.cpp:88-90
+            throw std::runtime_error("Input and/or output arrays do not have expected sizes");
+        }
+        std::lock_guard<std::mutex> lock(g_host_mutex);
+        std::vector<int32_t> key;
+        key.push_back(kind);
+        key.insert(key.end(), dims, dims + rank);
+        sstc_fft_plan_s *p = nullptr;
+        auto it = g_host_plans.find(key);
+        if (it == g_host_plans.end()) {
+            p = new sstc_fft_plan_s();
+            p->kind = kind;
+            p->dims.assign(dims, dims + rank);
+            p->in_len = a;
+            p->out_len = b;
+            try {
+                build_plan(*p);
+            } catch (...) {
+                delete p;
+                throw;
+            }
+            g_host_plans[key] = p;
+        } else {
+            p = it->second;
+        }
+        double *d_in = static_cast<double *>(g_host_in.get(a * 8));
+        double *d_out = static_cast<double *>(g_host_out.get(b * 8));
+        SSTC_CUDA(cudaMemcpyAsync(d_in, in, (size_t) a * 8, cudaMemcpyHostToDevice, 0));
+        execute_plan(*p, d_in, d_out, 0);
+        SSTC_CUDA(cudaMemcpyAsync(out, d_out, (size_t) b * 8, cudaMemcpyDeviceToHost, 0));
+        SSTC_CUDA(cudaStreamSynchronize(0));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// sstc_core.cu -- library lifecycle, error reporting and device-memory helpers of the C ABI.
+#include <string.h>
+
+#include "sstc_internal.h"
+
+namespace sstc {
+
+static thread_local std::string t_last_error;
+std::atomic<int64_t> g_launch_count{0};
+
+void set_last_error(const std::string &msg) { t_last_error = msg; }
+void clear_last_error() { t_last_error.clear(); }
+
+void *Scratch::get(int64_t need) {
+    if (need > bytes) {
+        if (ptr) {
+            cudaFree(ptr);
+            ptr = nullptr;
+            bytes = 0;
+        }
+        SSTC_CUDA(cudaMalloc(&ptr, (size_t) need));
+        bytes = need;
+    }
+    return ptr;
+}
+
+Scratch::~Scratch() {
+    // Process teardown: the CUDA context may already be gone; leak rather than call into a dead runtime.
+}
+
+}  // namespace sstc
+
+using namespace sstc;
+
+extern "C" {
+
+int sstc_init(int device) {
+    return guarded([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            throw std::runtime_error(
+                    std::string("no CUDA device: libsst_cuda has no CPU fallback (") + cudaGetErrorString(e) + ")");
+        }
+        if (device < 0 || device >= n) {
+            throw std::runtime_error("Invalid device");
+        }
+        SSTC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SSTC_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            throw std::runtime_error(std::string("libsst_cuda is built for sm_100a only; device is ") + prop.name);
+        }
+        SSTC_CUDA(cudaFree(0));
+    });
+}
+
+int sstc_shutdown(void) {
+    return guarded([&] { SSTC_CUDA(cudaDeviceSynchronize()); });
+}
+
+const char *sstc_last_error(void) { return t_last_error.c_str(); }
+
+int sstc_abi_version(void) { return SSTC_ABI_VERSION; }
+
+int64_t sstc_launch_count(void) { return g_launch_count.load(); }
+
+int sstc_malloc(void **dptr, int64_t bytes) {
+    return guarded([&] {
+        if (!dptr || bytes < 0) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        *dptr = nullptr;
+        if (bytes > 0) {
+            SSTC_CUDA(cudaMalloc(dptr, (size_t) bytes));
+        }
+    });
+}
+
+int sstc_free(void *dptr) {
+    return guarded([&] {
+        if (dptr) {
+            SSTC_CUDA(cudaFree(dptr));
+        }
+    });
+}
+
+int sstc_host_alloc(void **hptr, int64_t bytes) {
+    return guarded([&] {
+        if (!hptr || bytes < 0) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        *hptr = nullptr;
+        if (bytes > 0) {
+            SSTC_CUDA(cudaMallocHost(hptr, (size_t) bytes));
+        }
+    });
+}
+
+int sstc_host_free(void *hptr) {
+    return guarded([&] {
+        if (hptr) {
+            SSTC_CUDA(cudaFreeHost(hptr));
+        }
+    });
+}
+
+int sstc_h2d(void *dst, const void *src, int64_t bytes, void *stream) {
+    return guarded([&] {
+        SSTC_CUDA(cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    });
+}
+
+int sstc_d2h(void *dst, const void *src, int64_t bytes, void *stream) {
+    return guarded([&] {
+        SSTC_CUDA(cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    });
+}
+
+int sstc_d2d(void *dst, const void *src, int64_t bytes, void *stream) {
+    return guarded([&] {
+        SSTC_CUDA(cudaMemcpyAsync(dst, src, (size_t) bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    });
+}
+
+int sstc_memset(void *dst, int value, int64_t bytes, void *stream) {
+    return guarded([&] { SSTC_CUDA(cudaMemsetAsync(dst, value, (size_t) bytes, as_stream(stream))); });
+}
+
+int sstc_ipc_export(void *dptr, unsigned char handle[SSTC_IPC_HANDLE_BYTES]) {
+    return guarded([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == SSTC_IPC_HANDLE_BYTES, "handle size");
+        if (!dptr || !handle) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        cudaIpcMemHandle_t h;
+        SSTC_CUDA(cudaIpcGetMemHandle(&h, dptr));
+        memcpy(handle, &h, sizeof(h));
+    });
+}
+
+int sstc_ipc_open(const unsigned char handle[SSTC_IPC_HANDLE_BYTES], void **dptr) {
+    return guarded([&] {
+        if (!dptr || !handle) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof(h));
+        SSTC_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    });
+}
+
+int sstc_ipc_close(void *dptr) {
+    return guarded([&] {
+        if (dptr) {
+            SSTC_CUDA(cudaIpcCloseMemHandle(dptr));
+        }
+    });
+}
+
+int sstc_stream_sync(void *stream) {
+    return guarded([&] { SSTC_CUDA(cudaStreamSynchronize(as_stream(stream))); });
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""Slab-decomposed 3-D complex128 FFT over the GPUs of one box (one process per GPU).
+
+The reference has no distributed path; this is the one exchange step the
+north star adds. Layout contract, for dims (d0, d1, d2) over P ranks (P divides d0 and d1):
+
+    natural slabs      rank g holds x[g*d0/P:(g+1)*d0/P, :, :]            (a contiguous range of the flat array)
+    transposed slabs   rank g holds X[:, g*d1/P:(g+1)*d1/P, :]            (like FFTW-MPI TRANSPOSED_OUT)
+
+forward(): natural -> transposed.  z pass and y pass are local to a slab; the y pass does not store its
+result locally but scatters block q of the y axis straight to rank q (sstc_fft_axis_blocked_dev), so pack,
+transfer and unpack are part of the FFT kernel's store; the x pass then runs on the received
+(d0, d1/P, d2) array. inverse(): transposed -> natural, mirrored (x pass scatters x blocks to their owners).
+
+Two exchange modes:
+    "p2p"         destination blocks are the peers' receive buffers, mapped through CUDA IPC; the kernel
+                  stores over NVLink. One cross-rank barrier per transform (receive buffers are double-buffered).
+    "collective"  destination blocks are a local send buffer; torch.distributed all_to_all_single moves them
+                  (NCCL on GPUs, gloo in the CPU tests). Baseline and fallback for the host-logic tests.
+
+The local passes run through an engine: `CudaEngine` (the C ABI) here; the gloo tests under tests/ plug a
+numpy engine into the same host logic.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+class CudaEngine:
+    """Axis passes on CUDA tensors / raw device pointers through libsst_cuda.so."""
+
+    def __init__(self, device):
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        _lib.init(self.device.index or 0)
+
+    def empty(self, n_complex):
+        return torch.empty((int(n_complex), 2), dtype=torch.float64, device=self.device)
+
+    @staticmethod
+    def _ptr(x):
+        return int(x.data_ptr()) if isinstance(x, torch.Tensor) else int(x)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def axis(self, src, dst, outer, length, inner, inverse=False, scale=1.0):
+        _lib.check(_lib.lib().sstc_fft_axis_dev(
+            ctypes.c_void_p(self._ptr(src)), ctypes.c_void_p(self._ptr(dst)), int(outer), int(length), int(inner),
+            int(bool(inverse)), float(scale), ctypes.c_void_p(self._stream())))
+
+    def axis_blocked(self, src_blocks, src_pitch, dst_blocks, dst_pitch, outer, length, inner, inverse=False,
+                     scale=1.0):
+        sp = (ctypes.c_void_p * len(src_blocks))(*[self._ptr(b) for b in src_blocks])
+        dp = (ctypes.c_void_p * len(dst_blocks))(*[self._ptr(b) for b in dst_blocks])
+        _lib.check(_lib.lib().sstc_fft_axis_blocked_dev(
+            sp, len(src_blocks), int(src_pitch), dp, len(dst_blocks), int(dst_pitch), int(outer), int(length),
+            int(inner), int(bool(inverse)), float(scale), ctypes.c_void_p(self._stream())))
+
+
+class _DeviceArray:
+    """A raw device allocation seen by torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, n_complex):
+        self.__cuda_array_interface__ = {"shape": (int(n_complex), 2), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3}
+
+
+class PeerBuffer:
+    """A cudaMalloc'd buffer of n complex128 values that every rank of `group` maps (CUDA IPC)."""
+
+    def __init__(self, n_complex, device, group):
+        lib = _lib.lib()
+        self.n = int(n_complex)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        p = ctypes.c_void_p()
+        _lib.check(lib.sstc_malloc(ctypes.byref(p), self.n * 16))
+        self.local_ptr = p.value
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(lib.sstc_ipc_export(ctypes.c_void_p(self.local_ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+            else:
+                q = ctypes.c_void_p()
+                _lib.check(lib.sstc_ipc_open(h, ctypes.byref(q)))
+                self.ptrs.append(q.value)
+        self.tensor = torch.as_tensor(_DeviceArray(self.local_ptr, self.n), device=device)
+
+    def close(self):
+        lib = _lib.lib()
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                lib.sstc_ipc_close(ctypes.c_void_p(p))
+        if self.local_ptr:
+            lib.sstc_free(ctypes.c_void_p(self.local_ptr))
+        self.ptrs, self.local_ptr = [], None
+
+
+def block_ptrs(base, n_blocks, block_elems):
+    """Pointers (or tensor views) of n consecutive blocks of `block_elems` complex values inside `base`."""
+    if isinstance(base, torch.Tensor):
+        return [base[q * block_elems:(q + 1) * block_elems] for q in range(n_blocks)]
+    return [int(base) + q * block_elems * 16 for q in range(n_blocks)]
+
+
+class SlabFft3d:
+    """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
+
+    def __init__(self, dims, group=None, exchange="p2p", engine=None, device=None):
+        if len(dims) != 3:
+            raise ValueError("SlabFft3d needs three dimensions")
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.d0, self.d1, self.d2 = (int(d) for d in dims)
+        p = self.world
+        if self.d0 % p or self.d1 % p or p > 8:
+            raise ValueError("the rank count must divide d0 and d1 and be at most 8")
+        self.x_loc, self.y_loc = self.d0 // p, self.d1 // p
+        self.n_local = self.x_loc * self.d1 * self.d2          # == d0 * y_loc * d2
+        self.block = self.x_loc * self.y_loc * self.d2         # complex values per pairwise block
+        self.n_total = self.d0 * self.d1 * self.d2
+        self.exchange = exchange
+        self.engine = engine if engine is not None else CudaEngine(device if device is not None else 0)
+        self.work = self.engine.empty(self.n_local)
+        self._step = 0
+        if exchange == "p2p":
+            dev = self.engine.device
+            self.peer = [PeerBuffer(self.n_local, dev, group) for _ in range(2)]
+            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        elif exchange == "collective":
+            self.send = self.engine.empty(self.n_local)
+            self.recv = self.engine.empty(self.n_local)
+        else:
+            raise ValueError("exchange must be 'p2p' or 'collective'")
+
+    # -- cross-rank ordering ----------------------------------------------------------------------------
+    def _barrier(self):
+        # stream-ordered: the collective starts after this rank's scatter kernel and the next pass starts
+        # after every rank has joined, i.e. after every peer's stores into this rank's buffer are complete.
+        dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
+
+    # -- transforms ---------------------------------------------------------------------------------------
+    def forward(self, x):
+        """x: this rank's natural slab, (n_local, 2) float64. Returns this rank's transposed slab (a view
+        of an internal buffer, valid until the next-but-one call)."""
+        e, p = self.engine, self.world
+        e.axis(x, self.work, self.x_loc * self.d1, self.d2, 1)                                   # z
+        if self.exchange == "p2p":
+            buf = self.peer[self._step % 2]
+            self._step += 1
+            dst = [buf.ptrs[q] + self.rank * self.block * 16 for q in range(p)]
+            e.axis_blocked([self.work], 0, dst, 0, self.x_loc, self.d1, self.d2)                 # y + transpose
+            self._barrier()
+            out = buf.tensor
+        else:
+            e.axis_blocked([self.work], 0, block_ptrs(self.send, p, self.block), 0, self.x_loc, self.d1, self.d2)
+            dist.all_to_all_single(self.recv, self.send, group=self.group)
+            out = self.recv
+        e.axis(out, out, 1, self.d0, self.y_loc * self.d2)                                       # x
+        return out
+
+    def inverse(self, y):
+        """y: this rank's transposed slab. Returns this rank's natural slab of ifft (scaled by 1/N)."""
+        e, p = self.engine, self.world
+        row = self.d1 * self.d2  # one x row of a natural slab
+        if self.exchange == "p2p":
+            buf = self.peer[self._step % 2]
+            self._step += 1
+            # x block q -> rank q, landing at columns [rank*y_loc*d2, ...) of each of its x rows
+            dst = [buf.ptrs[q] + self.rank * self.y_loc * self.d2 * 16 for q in range(p)]
+            e.axis_blocked([y], 0, dst, row, 1, self.d0, self.y_loc * self.d2, inverse=True)    # x + transpose
+            self._barrier()
+            slab = buf.tensor
+            e.axis(slab, slab, self.x_loc, self.d1, self.d2, inverse=True)                       # y
+        else:
+            e.axis_blocked([y], 0, block_ptrs(self.send, p, self.block), 0, 1, self.d0, self.y_loc * self.d2,
+                           inverse=True)
+            dist.all_to_all_single(self.recv, self.send, group=self.group)
+            # the y axis arrives as one (x_loc, y_loc, d2) block per source rank
+            slab = self.work
+            e.axis_blocked(block_ptrs(self.recv, p, self.block), 0, [slab], 0, self.x_loc, self.d1, self.d2,
+                           inverse=True)
+        e.axis(slab, slab, self.x_loc * self.d1, self.d2, 1, inverse=True, scale=1.0 / self.n_total)  # z
+        return slab
+
+    def launches_per_forward(self):
+        return 3
+
+    def close(self):
+        if self.exchange == "p2p":
+            for b in self.peer:
+                b.close()
+
+
+def gather_transposed(shards, dims):
+    """Reassemble the full (d0, d1, d2, 2) array from the ranks' transposed slabs (test / verification helper)."""
+    d0, d1, d2 = dims
+    p = len(shards)
+    return torch.cat([s.reshape(d0, d1 // p, d2, 2) for s in shards], dim=1)
