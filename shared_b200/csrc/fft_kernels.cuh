@@ -31,7 +31,8 @@ enum FftMode : int { MODE_C2C = 0, MODE_R2C = 1, MODE_C2R = 2 };
 struct FftPassArgs {
     const double2 *in;   // c2c / c2r: complex input; r2c: reinterpret as const double*
     double2 *out;        // c2c / r2c: complex output; c2r: reinterpret as double*
-    const double2 *tw;   // tw[m] = exp(-2 pi i m / L), m in [0, L)
+    const double2 *tw;   // generic kernel: tw[m] = exp(-2 pi i m / L), m in [0, L)
+                         // pow2 kernel: stage-major table, see pow2_twiddle_count()
     int64_t outer;       // number of (L x inner) planes
     int64_t inner;       // stride between consecutive points of a line, in elements
     int64_t in_plane;    // elements between consecutive planes of the input (== L*inner unless sub-viewed)
@@ -113,6 +114,20 @@ __device__ __forceinline__ void dftR(double2 *v) {
 
 __host__ __device__ constexpr int fft_pad(int pos) { return pos + (pos >> 3); }
 
+// Radix of the Stockham stage that starts with `ns` already-combined points (radix 8 while it fits).
+__host__ __device__ constexpr int pow2_stage_radix(int L, int ns) { return (L / ns) >= 8 ? 8 : (L / ns); }
+
+// The pow2 kernel's twiddle table is stage-major so that a warp's lanes (consecutive k) read consecutive
+// 16-byte entries: for every stage after the first, entries [(r-1)*NS + k] = exp(-2 pi i r k / (NS*R)),
+// r = 1..R-1, k = 0..NS-1, stages concatenated in execution order.
+__host__ __device__ constexpr int pow2_twiddle_count(int L) {
+    int total = 0;
+    for (int ns = pow2_stage_radix(L, 1); ns < L; ns *= pow2_stage_radix(L, ns)) {
+        total += (pow2_stage_radix(L, ns) - 1) * ns;
+    }
+    return total;
+}
+
 // Tile geometry shared by host (launch configuration) and device.
 template <int L, int C, bool STRIDED>
 struct Pow2Tile {
@@ -146,7 +161,7 @@ struct Pow2Stages {
                 int k = (t + b * T) & (NS - 1);
 #pragma unroll
                 for (int r = 1; r < R; r++) {
-                    double2 w = __ldg(&tw[r * k * (L / (NS * R))]);
+                    double2 w = __ldg(&tw[(r - 1) * NS + k]);  // w_{NS*R}^{r*k}; lanes read consecutive k
                     v[b + r * B] = cmul(v[b + r * B], w);
                 }
             }
@@ -174,7 +189,8 @@ struct Pow2Stages {
             for (int m = 0; m < 8; m++) {
                 v[m] = sm[sidx(t + m * T, c)];
             }
-            Pow2Stages<L, C, STRIDED, (NS * R < L ? NS * R : L)>::run(v, t, c, sm, tw);
+            Pow2Stages<L, C, STRIDED, (NS * R < L ? NS * R : L)>::run(v, t, c, sm,
+                    tw + (NS > 1 ? (R - 1) * NS : 0));
         }
     }
 };

@@ -7,6 +7,7 @@
 // other axis in place on `out`; the inverse applies 1/N in the last pass. The reference's per-dimension
 // loop (FftOps.java:65-84) visits the same axes, rotating the layout each time instead.
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -20,38 +21,77 @@ namespace sstc {
 // ---- twiddle tables -----------------------------------------------------------------------------------
 
 static std::mutex g_tw_mutex;
-static std::map<std::pair<int, int>, double2 *> g_tw_cache;  // (device, L) -> table
+static std::map<std::pair<int, int>, double2 *> g_tw_cache;  // (device, +-L) -> table (-L: stage-major pow2)
 
-// tw[m] = exp(-2 pi i m / L), evaluated in long double then rounded (FftOps.java:155-168 uses double
-// cos/sin of a double phase; this is at least as accurate).
+static double2 unit_root(int64_t num, int64_t den) {
+    // exp(-2 pi i num/den), evaluated in long double then rounded (FftOps.java:155-168 uses double cos/sin
+    // of a double phase; this is at least as accurate). Exact values stay exact.
+    num %= den;
+    if (num == 0) {
+        return make_double2(1.0, 0.0);
+    }
+    if (4 * num == den) {
+        return make_double2(0.0, -1.0);
+    }
+    if (2 * num == den) {
+        return make_double2(-1.0, 0.0);
+    }
+    if (4 * num == 3 * den) {
+        return make_double2(0.0, 1.0);
+    }
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    long double ang = two_pi * (long double) num / (long double) den;
+    return make_double2((double) cosl(ang), (double) -sinl(ang));
+}
+
+static const double2 *upload_table(int key_len, const std::vector<double2> &host) {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    double2 *d = nullptr;
+    SSTC_CUDA(cudaMalloc(&d, sizeof(double2) * (host.empty() ? 1 : host.size())));
+    if (!host.empty()) {
+        SSTC_CUDA(cudaMemcpy(d, host.data(), sizeof(double2) * host.size(), cudaMemcpyHostToDevice));
+    }
+    g_tw_cache[std::make_pair(dev, key_len)] = d;
+    return d;
+}
+
+// Full-circle table for the any-length kernel: tw[m] = exp(-2 pi i m / L).
 static const double2 *twiddles_for(int L) {
     int dev = 0;
     SSTC_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_tw_mutex);
-    auto key = std::make_pair(dev, L);
-    auto it = g_tw_cache.find(key);
+    auto it = g_tw_cache.find(std::make_pair(dev, L));
     if (it != g_tw_cache.end()) {
         return it->second;
     }
     std::vector<double2> host((size_t) L);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
     for (int m = 0; m < L; m++) {
-        // octant symmetry keeps exact values (0, +-1, +-sqrt(1/2)) exact
-        long double ang = two_pi * (long double) m / (long double) L;
-        host[(size_t) m] = make_double2((double) cosl(ang), (double) -sinl(ang));
+        host[(size_t) m] = unit_root(m, L);
     }
-    if (L % 4 == 0) {
-        host[(size_t) (L / 4)] = make_double2(0.0, -1.0);
-        host[(size_t) (L / 2)] = make_double2(-1.0, 0.0);
-        host[(size_t) (3 * (L / 4))] = make_double2(0.0, 1.0);
-    } else if (L % 2 == 0) {
-        host[(size_t) (L / 2)] = make_double2(-1.0, 0.0);
+    return upload_table(L, host);
+}
+
+// Stage-major table for the pow2 kernel (layout: pow2_twiddle_count in fft_kernels.cuh).
+static const double2 *pow2_twiddles_for(int L) {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto it = g_tw_cache.find(std::make_pair(dev, -L));
+    if (it != g_tw_cache.end()) {
+        return it->second;
     }
-    double2 *d = nullptr;
-    SSTC_CUDA(cudaMalloc(&d, sizeof(double2) * (size_t) L));
-    SSTC_CUDA(cudaMemcpy(d, host.data(), sizeof(double2) * (size_t) L, cudaMemcpyHostToDevice));
-    g_tw_cache[key] = d;
-    return d;
+    std::vector<double2> host;
+    host.reserve((size_t) pow2_twiddle_count(L));
+    for (int ns = pow2_stage_radix(L, 1); ns < L; ns *= pow2_stage_radix(L, ns)) {
+        const int R = pow2_stage_radix(L, ns);
+        for (int r = 1; r < R; r++) {
+            for (int k = 0; k < ns; k++) {
+                host.push_back(unit_root((int64_t) r * k, (int64_t) ns * R));
+            }
+        }
+    }
+    return upload_table(-L, host);
 }
 
 // ---- axis-pass dispatch ------------------------------------------------------------------------------
@@ -83,6 +123,29 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
 
 template <int L>
 static void launch_pow2_L(const FftPassArgs &a, bool strided, cudaStream_t stream) {
+    if (L == 512) {
+        // Tile-width experiments for the headline length (env SSTC_FFT512_{STRIDED,CONTIG}_C); the defaults
+        // below are the measured winners.
+        static const int sc = getenv("SSTC_FFT512_STRIDED_C") ? atoi(getenv("SSTC_FFT512_STRIDED_C")) : 0;
+        static const int cc = getenv("SSTC_FFT512_CONTIG_C") ? atoi(getenv("SSTC_FFT512_CONTIG_C")) : 0;
+        if (strided && (sc == 4 || sc == 16)) {
+            int64_t tiles = (a.inner + sc - 1) / sc;
+            if (sc == 4) {
+                launch_pow2<512, 4, true>(a, a.outer * tiles, stream);
+            } else {
+                launch_pow2<512, 16, true>(a, a.outer * tiles, stream);
+            }
+            return;
+        }
+        if (!strided && (cc == 2 || cc == 8)) {
+            if (cc == 2) {
+                launch_pow2<512, 2, false>(a, (a.outer + 1) / 2, stream);
+            } else {
+                launch_pow2<512, 8, false>(a, (a.outer + 7) / 8, stream);
+            }
+            return;
+        }
+    }
     if (strided) {
         constexpr int C = strided_cols(L);
         int64_t tiles = (a.inner + C - 1) / C;
@@ -155,7 +218,8 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     FftPassArgs a;
     a.in = static_cast<const double2 *>(in);
     a.out = static_cast<double2 *>(out);
-    a.tw = twiddles_for(L);
+    const bool pow2 = L >= 8 && L <= 4096 && (L & (L - 1)) == 0;
+    a.tw = pow2 ? pow2_twiddles_for(L) : twiddles_for(L);
     a.outer = outer;
     a.inner = inner;
     a.in_plane = (int64_t) L * inner;
@@ -326,7 +390,12 @@ static void build_plan(sstc_fft_plan_s &p) {
     }
     // Build every twiddle table now so execute() never allocates.
     for (const Step &s : p.steps) {
-        twiddles_for(s.axis_len);
+        const int L = s.axis_len;
+        if (L >= 8 && L <= 4096 && (L & (L - 1)) == 0) {
+            pow2_twiddles_for(L);
+        } else {
+            twiddles_for(L);
+        }
     }
 }
 
