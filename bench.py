@@ -220,8 +220,8 @@ def run_ours(args):
     passes = []
     if world == 1:
         plan = shared_b200.FftPlan(shared_b200.FORWARD, DIMS, device=local)
-        if args.chunk_planes:
-            plan.set_hint("chunk_planes", args.chunk_planes)
+        if args.transposed_passes is not None:
+            plan.set_hint("transposed_passes", args.transposed_passes)
         y = torch.empty_like(x)
 
         def step():
@@ -268,12 +268,24 @@ def run_ours(args):
     if world == 1:
         reps = max(5, min(K, 20))
         d0, d1, d2 = DIMS
-        specs = [("z (contiguous axis)", x, y, d0 * d1, d2, 1), ("y (stride d2)", y, y, d0, d1, d2),
-                 ("x (stride d1*d2)", y, y, 1, d0, d1 * d2)]
         bytes_per_launch = 32.0 * n  # 16 B read + 16 B written per complex point
-        for name, src, dst, outer, length, inner in specs:
-            f = (lambda s=src, d=dst, o=outer, ln=length, i=inner:
-                 shared_b200.fft_axis(s.data_ptr(), d.data_ptr(), o, ln, i, False, 1.0, stream))
+        if plan.workspace_bytes:  # transposed schedule: time the passes exactly as the plan issues them
+            w = torch.empty_like(x)
+            pl = d1 * d2
+            specs = [("z (contiguous axis)", lambda: shared_b200.fft_axis(x.data_ptr(), y.data_ptr(), d0 * d1, d2, 1,
+                                                                          False, 1.0, stream)),
+                     ("y (stride d2, transposed store)", lambda: shared_b200.fft_axis_strided(
+                         y.data_ptr(), w.data_ptr(), d0, d1, d2, pl, d2, d2, d0 * d2, False, 1.0, stream)),
+                     ("x (stride d2 after transpose, natural store)", lambda: shared_b200.fft_axis_strided(
+                         w.data_ptr(), y.data_ptr(), d1, d0, d2, d0 * d2, d2, d2, pl, False, 1.0, stream))]
+        else:
+            specs = [("z (contiguous axis)", lambda: shared_b200.fft_axis(x.data_ptr(), y.data_ptr(), d0 * d1, d2, 1,
+                                                                          False, 1.0, stream)),
+                     ("y (stride d2)", lambda: shared_b200.fft_axis(y.data_ptr(), y.data_ptr(), d0, d1, d2, False,
+                                                                    1.0, stream)),
+                     ("x (stride d1*d2)", lambda: shared_b200.fft_axis(y.data_ptr(), y.data_ptr(), 1, d0, d1 * d2,
+                                                                       False, 1.0, stream))]
+        for name, f in specs:
             f()
             ms = event_ms(f, reps, torch)
             passes.append({"pass": name, "ms": ms, "gbs": bytes_per_launch / ms / 1e6})
@@ -332,7 +344,8 @@ def run_ours(args):
             "config": {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward), device-resident",
                        "dims": list(DIMS), "parallelism": parallelism,
                        "l2": "inputs larger than L2 (2 GiB in + 2 GiB out vs 126 MB), no flush needed",
-                       "chunk_planes": args.chunk_planes if world == 1 else None},
+                       "schedule": ("z in->out, y out->workspace (transposed store), x workspace->out"
+                                    if world == 1 and plan.workspace_bytes else "one pass per axis, in place after the first")},
             "hbm_model_gbs": 3 * 32.0 * n / ms_step / 1e6,
             "gpu_launches": int(launches), "launches_per_step": launches_per_step,
             "e2e": {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
@@ -358,7 +371,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--exchange", choices=["p2p", "collective"], default="p2p")
-    ap.add_argument("--chunk-planes", type=int, default=0, dest="chunk_planes")
+    ap.add_argument("--transposed-passes", type=int, default=None, dest="transposed_passes",
+                    help="plan hint: -1 auto (default), 0 never, 1 always")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

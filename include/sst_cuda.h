@@ -78,9 +78,10 @@ int sstc_fft_plan_destroy(sstc_fft_plan plan);
 /* Bytes of device workspace the plan owns, and the number of kernel launches one execute issues. */
 int64_t sstc_fft_plan_workspace(sstc_fft_plan plan);
 int sstc_fft_plan_launches(sstc_fft_plan plan);
-/* Plan tunables (FftService.setHint analogue; FftwService.java:93-143). Known names: "chunk_planes"
- * (planes per L2-resident chunk of the fused last-two-axes schedule; 0 = one launch per axis). Unknown
- * names fail with "Unknown hint" (JavaFftService.java:96-104). */
+/* Plan tunables (FftService.setHint analogue; FftwService.java:93-143). Known names: "transposed_passes"
+ * (c2c, rank >= 3: the two outermost passes exchange their data through a transposed workspace so that
+ * neither loads with the outermost stride; -1 = automatic, 0 = never, 1 = whenever legal). Unknown names
+ * fail with "Unknown hint" (JavaFftService.java:96-104). Not thread-safe against a concurrent execute. */
 int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value);
 
 /* One axis pass of a row-major complex array viewed as (outer, len, inner): the building block the
@@ -88,6 +89,14 @@ int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value);
  * `inverse` selects e^{+2 pi i jk/n}; every output is multiplied by `scale`. In place when d_in == d_out. */
 int sstc_fft_axis_dev(const double *d_in, double *d_out, int64_t outer, int32_t len, int64_t inner, int inverse,
         double scale, void *stream);
+
+/* The same pass with explicit layouts: point k of line (o, i) is read at o*in_plane + k*in_kstride + i and
+ * written at o*out_plane + k*out_kstride + i (complex elements; columns i stay contiguous). Lets a pass
+ * transpose while it transforms, e.g. read (o,k,i) and write (k,o,i). Out of place only unless the two
+ * layouts are identical. */
+int sstc_fft_axis_strided_dev(const double *d_in, double *d_out, int64_t outer, int32_t len, int64_t inner,
+        int64_t in_plane, int64_t in_kstride, int64_t out_plane, int64_t out_kstride, int inverse, double scale,
+        void *stream);
 
 /* The same pass with blocked addressing on either side. The axis is cut into n equal blocks of len/n points;
  * point k of plane o, column i lives at blocks[k / (len/n)] + (o*(len/n) + k % (len/n))*pitch + i (complex

@@ -44,6 +44,9 @@ SIGNATURES = {
     "sstc_fft_plan_set_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "sstc_fft_axis_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                          ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
+    "sstc_fft_axis_strided_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                 ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                 ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
     "sstc_fft_axis_blocked_dev": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int64, c_void_pp, ctypes.c_int,
                                                  ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                                  ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),

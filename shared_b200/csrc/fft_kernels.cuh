@@ -37,6 +37,8 @@ struct FftPassArgs {
     int64_t inner;       // stride between consecutive points of a line, in elements
     int64_t in_plane;    // elements between consecutive planes of the input (== L*inner unless sub-viewed)
     int64_t out_plane;
+    int64_t in_kstride;  // STRIDED: elements between consecutive points of a line (== inner unless the pass
+    int64_t out_kstride; //          also transposes, e.g. reads (o,k,i) and writes (k,o,i))
     double scale;        // applied on store
     int mode;            // FftMode
     int inverse;         // 0: e^{-i..}, 1: e^{+i..}
@@ -219,7 +221,7 @@ fft_pow2_kernel(const FftPassArgs a) {
 
     // Locate the tile. STRIDED: blockIdx.x -> (plane o, column tile); CONTIG: blockIdx.x -> C lines.
     bool active;
-    int64_t in_base, out_base, estride;
+    int64_t in_base, out_base, in_ks, out_ks;
     int64_t line = 0;  // CONTIG line number (for r2c / c2r addressing)
     int64_t o = 0, i = 0;
     if (STRIDED) {
@@ -229,13 +231,14 @@ fft_pow2_kernel(const FftPassArgs a) {
         active = i < a.inner;
         in_base = o * a.in_plane + i;
         out_base = o * a.out_plane + i;
-        estride = a.inner;
+        in_ks = a.in_kstride;
+        out_ks = a.out_kstride;
     } else {
         line = (int64_t) blockIdx.x * C + c;
         active = line < a.outer;
         in_base = line * a.in_plane;
         out_base = line * a.out_plane;
-        estride = 1;
+        in_ks = out_ks = 1;
     }
 
     double2 v[8];
@@ -251,7 +254,7 @@ fft_pow2_kernel(const FftPassArgs a) {
         } else if (a.mode == MODE_C2C) {
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                v[m] = a.in[in_base + (int64_t) (t + m * T) * estride];
+                v[m] = a.in[in_base + (int64_t) (t + m * T) * in_ks];
             }
         } else if (a.mode == MODE_R2C) {
             const double *rin = reinterpret_cast<const double *>(a.in) + line * L;
@@ -304,7 +307,7 @@ fft_pow2_kernel(const FftPassArgs a) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
-            a.out[out_base + (int64_t) (t + m * T) * estride] = z;
+            a.out[out_base + (int64_t) (t + m * T) * out_ks] = z;
         }
     } else if (a.mode == MODE_R2C) {
         double2 *hout = a.out + line * (L / 2 + 1);
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g
             const int pk = p - q * a.in_ksplit;
             z = a.in_blk[q][(o * a.in_ksplit + pk) * a.in_blk_pitch + i];
         } else if (a.mode == MODE_C2C) {
-            z = a.in[o * a.in_plane + (int64_t) p * a.inner + i];
+            z = a.in[o * a.in_plane + (int64_t) p * a.in_kstride + i];
         } else if (a.mode == MODE_R2C) {
             z = make_double2(reinterpret_cast<const double *>(a.in)[line * L + p], 0.0);
         } else {
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g
             const int pk = p - q * a.ksplit;
             a.blk[q][(o * a.ksplit + pk) * a.blk_pitch + i] = z;
         } else if (a.mode == MODE_C2C) {
-            a.out[o * a.out_plane + (int64_t) p * a.inner + i] = z;
+            a.out[o * a.out_plane + (int64_t) p * a.out_kstride + i] = z;
         } else if (a.mode == MODE_R2C) {
             if (p < half) {
                 a.out[line * half + p] = z;

@@ -127,3 +127,12 @@ def fft_axis(d_in, d_out, outer, length, inner, inverse=False, scale=1.0, stream
     _lib.check(_lib.lib().sstc_fft_axis_dev(ctypes.c_void_p(int(d_in)), ctypes.c_void_p(int(d_out)), int(outer),
                                             int(length), int(inner), int(bool(inverse)), float(scale),
                                             ctypes.c_void_p(int(stream))))
+
+
+def fft_axis_strided(d_in, d_out, outer, length, inner, in_plane, in_kstride, out_plane, out_kstride, inverse=False,
+                     scale=1.0, stream=0):
+    """One axis pass with explicit input/output layouts (sstc_fft_axis_strided_dev)."""
+    _lib.check(_lib.lib().sstc_fft_axis_strided_dev(
+        ctypes.c_void_p(int(d_in)), ctypes.c_void_p(int(d_out)), int(outer), int(length), int(inner), int(in_plane),
+        int(in_kstride), int(out_plane), int(out_kstride), int(bool(inverse)), float(scale),
+        ctypes.c_void_p(int(stream))))

@@ -190,8 +190,14 @@ def test_3d_device_properties(dims):
     bwd.execute(y.data_ptr(), z.data_ptr(), stream)
     err = (torch.linalg.norm(z - x) / torch.linalg.norm(x)).item()
     assert err < tol, err
-    # (5) the L2-chunked schedule is the same arithmetic: bit-identical output
-    fwd.set_hint("chunk_planes", 8)
+    # (5) the transposed-pass schedule and the in-place schedule are the same arithmetic: bit-identical
+    fwd.set_hint("transposed_passes", 0)
+    assert fwd.workspace_bytes == 0
+    fwd.execute(x.data_ptr(), z.data_ptr(), stream)
+    assert torch.equal(z, y)
+    fwd.set_hint("transposed_passes", 1)
+    assert fwd.workspace_bytes == 16 * n
+    z.zero_()
     fwd.execute(x.data_ptr(), z.data_ptr(), stream)
     assert torch.equal(z, y)
     # (6) a unit impulse at flat index j transforms to a pure phase of modulus 1

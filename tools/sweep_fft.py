@@ -1,5 +1,5 @@
 """Tuning sweep (run on the GPU box): per-pass and per-step CUDA-event times at 512^3 for the current
-SSTC_FFT512_* tile settings and a list of chunk_planes values."""
+SSTC_FFT512_* tile settings and both plan schedules."""
 import json
 import os
 import sys
@@ -36,9 +36,9 @@ res["y"] = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), 512, 512, 512, Fals
 res["x"] = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), 1, 512, 512 * 512, False, 1.0, st))
 res["copy"] = ev(lambda: y.copy_(x))
 plan = s.FftPlan(s.FORWARD, dims)
-for ch in [int(c) for c in (sys.argv[1:] or ["0", "2", "4", "8", "16", "32"])]:
-    plan.set_hint("chunk_planes", ch)
-    res["step_chunk%d" % ch] = ev(lambda: plan.execute(x.data_ptr(), y.data_ptr(), st))
+for tp in (0, 1):
+    plan.set_hint("transposed_passes", tp)
+    res["step_transposed%d" % tp] = ev(lambda: plan.execute(x.data_ptr(), y.data_ptr(), st))
 xc = torch.view_as_complex(x).reshape(dims)
 res["cufft_torch"] = ev(lambda: torch.fft.fftn(xc), 10)
 print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()}))
