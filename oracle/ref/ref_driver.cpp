@@ -1,0 +1,172 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- flat C entry points over the reference's own native ArrayKernel.
+ *
+ * oracle/Makefile compiles this file together with the UNMODIFIED sources
+ * /root/reference/native/src/shared/{Common,ElementOps,DimensionOps*,MappingOps*,MatrixOps,NativeArrayKernel,
+ * IndexOps}.cpp (read where they lie; never copied) against the shim oracle/ref/jni.h into
+ * oracle/_ref/libsst_ref.so. The parity tests call these wrappers; each one builds the {kind,data,len} array
+ * records the shim uses for Java arrays and forwards to the function the JNI export table binds
+ * (native/src/shared/Bindings.cpp:26-142). A Java exception shows up as return code 1 + sstref_last_error().
+ */
+#include <Bindings.hpp>
+
+#include <stdlib.h>
+
+#include <string>
+
+static std::string g_error;
+static bool g_init = false;
+
+static JNIEnv *env_get() {
+    static JNIEnv env;
+    if (!g_init) {
+        NativeArrayKernel::init(&env); /* caches the [D / [I class handles (NativeArrayKernel.cpp:37-57) */
+        g_init = true;
+    }
+    env.pending = false;
+    env.message.clear();
+    return &env;
+}
+
+static int env_done(JNIEnv *env) {
+    if (env->pending) {
+        g_error = env->message;
+        return 1;
+    }
+    g_error.clear();
+    return 0;
+}
+
+static _jobject arr(int kind, const void *data, int len) {
+    _jobject o;
+    o.kind = kind;
+    o.data = const_cast<void *>(data);
+    o.len = len;
+    o.owned = 0;
+    return o;
+}
+
+#define DARR(p, n) arr(SHIM_DOUBLE_ARRAY, p, n)
+#define IARR(p, n) arr(SHIM_INT_ARRAY, p, n)
+
+extern "C" {
+
+const char *sstref_last_error() { return g_error.c_str(); }
+
+void sstref_srand(unsigned seed) { srand(seed); }
+
+int sstref_ruop(int type, double a, double *v, int n) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(v, n);
+    ElementOps::ruOp(env, 0, type, a, &s);
+    return env_done(env);
+}
+
+int sstref_cuop(int type, double re, double im, double *v, int n) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(v, n);
+    ElementOps::cuOp(env, 0, type, re, im, &s);
+    return env_done(env);
+}
+
+int sstref_iuop(int type, int a, int *v, int n) {
+    JNIEnv *env = env_get();
+    _jobject s = IARR(v, n);
+    ElementOps::iuOp(env, 0, type, a, &s);
+    return env_done(env);
+}
+
+/* kind: SHIM_DOUBLE_ARRAY (1) or SHIM_INT_ARRAY (2) for all three operands */
+int sstref_eop(int type, int kind, const void *lhs, const void *rhs, void *dst, int n, int complex) {
+    JNIEnv *env = env_get();
+    _jobject l = arr(kind, lhs, n), r = arr(kind, rhs, n), d = arr(kind, dst, n);
+    ElementOps::eOp(env, 0, type, &l, &r, &d, complex ? JNI_TRUE : JNI_FALSE);
+    return env_done(env);
+}
+
+int sstref_convert(int type, const void *src, int src_kind, int nsrc, int src_complex, double *dst, int ndst,
+        int dst_complex) {
+    JNIEnv *env = env_get();
+    _jobject s = arr(src_kind, src, nsrc), d = DARR(dst, ndst);
+    ElementOps::convert(env, 0, type, &s, src_complex ? JNI_TRUE : JNI_FALSE, &d, dst_complex ? JNI_TRUE : JNI_FALSE);
+    return env_done(env);
+}
+
+int sstref_raop(int type, const double *v, int n, double *out) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(v, n);
+    *out = ElementOps::raOp(env, 0, type, &s);
+    return env_done(env);
+}
+
+int sstref_caop(int type, const double *v, int n, double out[2]) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(v, n);
+    jdoubleArray res = ElementOps::caOp(env, 0, type, &s);
+    if (res && res->len == 2) {
+        out[0] = ((double *) res->data)[0];
+        out[1] = ((double *) res->data)[1];
+        free(res->data);
+        free(res);
+    }
+    return env_done(env);
+}
+
+int sstref_rrop(int type, const double *src, int nsrc, const int *sD, const int *sS, int nd, double *dst, int ndst,
+        const int *dD, const int *dS, int *opDims, int nop) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), d = DARR(dst, ndst), dd = IARR(dD, nd),
+             ds = IARR(dS, nd), od = IARR(opDims, nop);
+    DimensionOps::rrOp(env, 0, type, &s, &sd, &ss, &d, &dd, &ds, &od);
+    return env_done(env);
+}
+
+int sstref_riop(int type, double *src, int nsrc, const int *sD, const int *sS, int nd, int *dst, int ndst, int dim) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), d = IARR(dst, ndst);
+    DimensionOps::riOp(env, 0, type, &s, &sd, &ss, &d, dim);
+    return env_done(env);
+}
+
+int sstref_rdop(int type, const double *src, int nsrc, const int *sD, const int *sS, int nd, double *dst, int ndst,
+        int *opDims, int nop) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), d = DARR(dst, ndst), od = IARR(opDims, nop);
+    DimensionOps::rdOp(env, 0, type, &s, &sd, &ss, &d, &od);
+    return env_done(env);
+}
+
+int sstref_map(const int *bounds, int nb, const void *src, int kind, int nsrc, const int *sD, const int *sS, int nds,
+        void *dst, int ndst, const int *dD, const int *dS, int ndd) {
+    JNIEnv *env = env_get();
+    _jobject b = IARR(bounds, nb), s = arr(kind, src, nsrc), sd = IARR(sD, nds), ss = IARR(sS, nds),
+             d = arr(kind, dst, ndst), dd = IARR(dD, ndd), ds = IARR(dS, ndd);
+    MappingOps::map(env, 0, &b, &s, &sd, &ss, &d, &dd, &ds);
+    return env_done(env);
+}
+
+int sstref_slice(const int *slices, int nsl, const void *src, int kind, int nsrc, const int *sD, const int *sS,
+        int nds, void *dst, int ndst, const int *dD, const int *dS, int ndd) {
+    JNIEnv *env = env_get();
+    _jobject b = IARR(slices, nsl), s = arr(kind, src, nsrc), sd = IARR(sD, nds), ss = IARR(sS, nds),
+             d = arr(kind, dst, ndst), dd = IARR(dD, ndd), ds = IARR(dS, ndd);
+    MappingOps::slice(env, 0, &b, &s, &sd, &ss, &d, &dd, &ds);
+    return env_done(env);
+}
+
+int sstref_mul(const double *lhs, int nl, const double *rhs, int nr, int lr, int rc, double *dst, int ndst,
+        int complex) {
+    JNIEnv *env = env_get();
+    _jobject l = DARR(lhs, nl), r = DARR(rhs, nr), d = DARR(dst, ndst);
+    MatrixOps::mul(env, 0, &l, &r, lr, rc, &d, complex ? JNI_TRUE : JNI_FALSE);
+    return env_done(env);
+}
+
+int sstref_diag(const double *src, int nsrc, double *dst, int ndst, int size, int complex) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), d = DARR(dst, ndst);
+    MatrixOps::diag(env, 0, &s, &d, size, complex ? JNI_TRUE : JNI_FALSE);
+    return env_done(env);
+}
+
+}  // extern "C"

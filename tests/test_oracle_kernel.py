@@ -1,0 +1,53 @@
+"""Pins the ArrayKernel oracle -- the reference's own native kernel compiled from /root/reference against the
+shim (oracle/_ref/libsst_ref.so) -- to the reference's Java-side known answers. CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden
+from kernel_kats import check_all
+
+ref = oracle.ref()
+pytestmark = pytest.mark.skipif(ref is None, reason="oracle/_ref/libsst_ref.so not built (needs /root/reference)")
+
+
+def test_call_level_kats():
+    assert check_all(ref) >= 50  # ArrayKernelTest.java:61-378
+
+
+def far(dims):
+    s = [1] * len(dims)
+    for i in range(len(dims) - 2, -1, -1):
+        s[i] = s[i + 1] * dims[i + 1]
+    return s
+
+
+def test_rrop_sum_kat():
+    # RealArrayTest.java:726-758: a.rSum(1) on 3x4x5 FAR
+    recs = golden("RealArrayTest")["testRrOps"]
+    a, exp = recs[0], recs[1]
+    src = np.array(a["values"])
+    dst = np.zeros(len(exp["values"]))
+    ref.rrOp(0, src, a["dims"], far(a["dims"]), dst, exp["dims"], far(exp["dims"]), 1)
+    assert np.array_equal(dst, np.array(exp["values"]))
+
+
+def test_mul_kat():
+    # MatrixTest.java:69-90: a (4x3) . a^T; :92-123: complex 3x5 . 5x3
+    recs = golden("MatrixTest")["testMMul"]
+    a, exp = recs[0], recs[1]
+    at = np.ascontiguousarray(np.array(a["values"]).reshape(4, 3).T).ravel()
+    dst = np.zeros(16)
+    ref.mul(np.array(a["values"]), at, 4, 4, dst, False)
+    assert np.max(np.abs(dst - np.array(exp["values"]))) < 1e-8
+    c1, c2, cexp = recs[2], recs[3], recs[4]
+    dst = np.zeros(18)
+    ref.mul(np.array(c1["values"]), np.array(c2["values"]), 3, 3, dst, True)
+    assert np.max(np.abs(dst - np.array(cexp["values"]))) < 1e-8
+
+
+def test_error_text():
+    with pytest.raises(oracle.refkernel.RefKernelError, match="Invalid dimensions and/or strides"):
+        ref.rrOp(0, np.zeros(6), [2, 3], [1, 1], np.zeros(2), [2, 1], [1, 1], 1)
+    with pytest.raises(oracle.refkernel.RefKernelError, match="Operation type not recognized"):
+        ref.ruOp(99, 0.0, np.zeros(3))
