@@ -115,6 +115,90 @@ int sstc_ipc_export(void *dptr, unsigned char handle[SSTC_IPC_HANDLE_BYTES]);
 int sstc_ipc_open(const unsigned char handle[SSTC_IPC_HANDLE_BYTES], void **dptr);
 int sstc_ipc_close(void *dptr);
 
+/* ---- ArrayKernel ------------------------------------------------------------------------------------
+ *
+ * One HOST-tier entry point per native method of org.shared.array.jni.NativeArrayKernel
+ * (src/org/shared/array/jni/NativeArrayKernel.java:56-154, JNI exports native/src/shared/Bindings.cpp:26-142),
+ * with the same argument order; a Java array becomes (pointer, length). `type` is the ArrayKernel opcode
+ * (src/org/shared/array/kernel/ArrayKernel.java:45-278). Validation and error messages follow the reference's
+ * C++ ("Invalid arguments", "Invalid dimensions and/or strides", "Invalid array lengths", "Operation type not
+ * recognized", "Duplicate operating dimensions are not allowed", "Operating dimensions must have singleton or
+ * zero length", "Invalid dimension", "Invalid index", "Invalid mapping parameters", "Invalid array types").
+ * dims / strides / bounds / slices / opDims are small HOST arrays in BOTH tiers. Every `_dev` twin takes device
+ * pointers for the value arrays plus a stream, and returns without synchronising (scratch is per host thread:
+ * issue one thread's calls on one stream). */
+
+/* element kinds for eOp (ElementOps.cpp:285-321 dispatches on the runtime array type and the complex flag) */
+#define SSTC_ELEM_REAL 0
+#define SSTC_ELEM_COMPLEX 1
+#define SSTC_ELEM_INT 2
+/* conversion families for convert (ElementOps.cpp:323-407) */
+#define SSTC_CONV_R_TO_C 0
+#define SSTC_CONV_C_TO_R 1
+#define SSTC_CONV_I_TO_R 2
+
+/* randomize / derandomize (Bindings.cpp:26-32; JavaArrayKernel.java:57-64): reseeds RND and SHUFFLE. */
+int sstc_srand(uint64_t seed);
+
+/* ruOp / cuOp / iuOp: in-place unary maps (Bindings.cpp:86-99). n = array length (doubles / ints). */
+int sstc_ruop(int type, double a, double *v, int64_t n);
+int sstc_cuop(int type, double re, double im, double *v, int64_t n);
+int sstc_iuop(int type, int32_t a, int32_t *v, int64_t n);
+int sstc_ruop_dev(int type, double a, double *v, int64_t n, void *stream);
+int sstc_cuop_dev(int type, double re, double im, double *v, int64_t n, void *stream);
+int sstc_iuop_dev(int type, int32_t a, int32_t *v, int64_t n, void *stream);
+
+/* eOp: dst = lhs (op) rhs, n = length of each array in its storage type; dst may alias lhs (Bindings.cpp:101-104). */
+int sstc_eop(int type, int elem, const void *lhs, const void *rhs, void *dst, int64_t n);
+int sstc_eop_dev(int type, int elem, const void *lhs, const void *rhs, void *dst, int64_t n, void *stream);
+
+/* convert (Bindings.cpp:106-109). */
+int sstc_convert(int type, int conv, const void *src, int64_t nsrc, double *dst, int64_t ndst);
+int sstc_convert_dev(int type, int conv, const void *src, int64_t nsrc, double *dst, int64_t ndst, void *stream);
+
+/* raOp -> one double, caOp -> {re, im} (Bindings.cpp:76-84). The _dev twins write to DEVICE memory. */
+int sstc_raop(int type, const double *v, int64_t n, double *out);
+int sstc_caop(int type, const double *v, int64_t n, double out[2]);
+int sstc_raop_dev(int type, const double *v, int64_t n, double *d_out, void *stream);
+int sstc_caop_dev(int type, const double *v, int64_t n, double *d_out2, void *stream);
+
+/* rrOp: reduce over opDims (sorted in place, as the reference does); dst keeps size-1 dims (Bindings.cpp:54-62). */
+int sstc_rrop(int type, const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, double *dst,
+        int64_t ndst, const int32_t *dD, const int32_t *dS, int nd, int32_t *opDims, int nop);
+int sstc_rrop_dev(int type, const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, double *dst,
+        int64_t ndst, const int32_t *dD, const int32_t *dS, int nd, int32_t *opDims, int nop, void *stream);
+
+/* riOp: positions along `dim` (or dim = -1: whole array); RI_SORT also sorts src in place (Bindings.cpp:64-70). */
+int sstc_riop(int type, double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, int32_t *dst,
+        int64_t ndst, int dim);
+int sstc_riop_dev(int type, double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, int32_t *dst,
+        int64_t ndst, int dim, void *stream);
+
+/* rdOp: inclusive prefix scan along each of opDims in ascending order (Bindings.cpp:72-74). */
+int sstc_rdop(int type, const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, double *dst,
+        int64_t ndst, const int32_t *opDims, int nop);
+int sstc_rdop_dev(int type, const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, double *dst,
+        int64_t ndst, const int32_t *opDims, int nop, void *stream);
+
+/* map / slice (Bindings.cpp:34-52): elem_bytes = 8 (double[]) or 4 (int[]); Object[] arrays stay on the JVM side. */
+int sstc_map(int elem_bytes, const int32_t *bounds, int nbounds, const void *src, int64_t nsrc, const int32_t *sD,
+        const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd);
+int sstc_map_dev(int elem_bytes, const int32_t *bounds, int nbounds, const void *src, int64_t nsrc, const int32_t *sD,
+        const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd, void *stream);
+int sstc_slice(int elem_bytes, const int32_t *slices, int nslices3, const void *src, int64_t nsrc, const int32_t *sD,
+        const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd);
+int sstc_slice_dev(int elem_bytes, const int32_t *slices, int nslices3, const void *src, int64_t nsrc,
+        const int32_t *sD, const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd,
+        void *stream);
+
+/* mul / diag (Bindings.cpp:111-119): row-major, inner dimension inferred from the lengths. */
+int sstc_mul(const double *lhs, int64_t nl, const double *rhs, int64_t nr, int lr, int rc, double *dst, int64_t ndst,
+        int complex);
+int sstc_mul_dev(const double *lhs, int64_t nl, const double *rhs, int64_t nr, int lr, int rc, double *dst, int64_t ndst,
+        int complex, void *stream);
+int sstc_diag(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex);
+int sstc_diag_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,28 @@ SIGNATURES = {
     "sstc_ipc_close": (ctypes.c_int, [ctypes.c_void_p]),
 }
 
+_vp, _i, _i64, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+_ARRAY_OPS = {
+    "sstc_ruop": [_i, _d, _vp, _i64],
+    "sstc_cuop": [_i, _d, _d, _vp, _i64],
+    "sstc_iuop": [_i, ctypes.c_int32, _vp, _i64],
+    "sstc_eop": [_i, _i, _vp, _vp, _vp, _i64],
+    "sstc_convert": [_i, _i, _vp, _i64, _vp, _i64],
+    "sstc_raop": [_i, _vp, _i64, _vp],
+    "sstc_caop": [_i, _vp, _i64, _vp],
+    "sstc_rrop": [_i, _vp, _i64, c_i32_p, c_i32_p, _vp, _i64, c_i32_p, c_i32_p, _i, c_i32_p, _i],
+    "sstc_riop": [_i, _vp, _i64, c_i32_p, c_i32_p, _i, _vp, _i64, _i],
+    "sstc_rdop": [_i, _vp, _i64, c_i32_p, c_i32_p, _i, _vp, _i64, c_i32_p, _i],
+    "sstc_map": [_i, c_i32_p, _i, _vp, _i64, c_i32_p, c_i32_p, _vp, _i64, c_i32_p, c_i32_p, _i],
+    "sstc_slice": [_i, c_i32_p, _i, _vp, _i64, c_i32_p, c_i32_p, _vp, _i64, c_i32_p, c_i32_p, _i],
+    "sstc_mul": [_vp, _i64, _vp, _i64, _i, _i, _vp, _i64, _i],
+    "sstc_diag": [_vp, _i64, _vp, _i64, _i, _i],
+}
+for _name, _args in _ARRAY_OPS.items():
+    SIGNATURES[_name] = (ctypes.c_int, _args)
+    SIGNATURES[_name + "_dev"] = (ctypes.c_int, _args + [ctypes.c_void_p])  # device twin: same arguments + stream
+SIGNATURES["sstc_srand"] = (ctypes.c_int, [ctypes.c_uint64])
+
 
 class SstCudaError(RuntimeError):
     """What the JNI glue raises as java.lang.RuntimeException (native/src/shared/Common.cpp:173-178)."""

@@ -1,0 +1,272 @@
+// array_mapping.cu -- ArrayKernel data movement on the device: n-D modular block copy (map) and Cartesian
+// gather/scatter (slice), plus matrix diagonal extraction.
+//
+// Replaces (paths relative to /root/reference):
+//   map    src/org/shared/array/kernel/MappingOps.java:196-266   native/src/shared/MappingOpsMap.cpp:26-195
+//   slice  MappingOps.java:271-336                               native/src/shared/MappingOpsSlice.cpp:26-195
+//   diag   MatrixOps.java:104-126                                native/src/shared/MatrixOps.cpp:100-152
+// The reference builds two int[] tables of physical indices (one per side) and then copies element by
+// element -- >= 32 B of traffic per 8 B moved. Here each thread derives both physical offsets from its map
+// index, so traffic is the 16 B / element minimum (8 B elements) and no table exists. Bit-exact by
+// construction (pure movement).
+#include <algorithm>
+#include <vector>
+
+#include "array_common.cuh"
+
+namespace sstc {
+
+struct MapSpec {
+    int nd;
+    int64_t total;
+    int32_t size[kMaxDims];      // map extent per dimension, last dimension fastest
+    int32_t sstart[kMaxDims], dstart[kMaxDims];
+    int32_t sdim[kMaxDims], ddim[kMaxDims];
+    int64_t sstride[kMaxDims], dstride[kMaxDims];
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) map_kernel(const T *__restrict__ src, T *dst, MapSpec M) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; m < M.total; m += stride) {
+        int64_t rem = m, soff = 0, doff = 0;
+        for (int d = M.nd - 1; d >= 0; d--) {
+            const int64_t q = rem / M.size[d];
+            const int j = (int) (rem - q * M.size[d]);
+            rem = q;
+            // indices wrap modulo the dimension on both sides (MappingOps.java:237-249)
+            soff += (int64_t) ((M.sstart[d] + j) % M.sdim[d]) * M.sstride[d];
+            doff += (int64_t) ((M.dstart[d] + j) % M.ddim[d]) * M.dstride[d];
+        }
+        dst[doff] = src[soff];
+    }
+}
+
+struct SliceSpec {
+    int nd;
+    int64_t total;
+    int32_t count[kMaxDims];
+    int32_t offset[kMaxDims];  // start of this dimension's (src, dst) index lists in the tables
+    int64_t sstride[kMaxDims], dstride[kMaxDims];
+};
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) slice_kernel(const T *__restrict__ src, T *dst, SliceSpec S,
+        const int32_t *__restrict__ sidx, const int32_t *__restrict__ didx) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; m < S.total; m += stride) {
+        int64_t rem = m, soff = 0, doff = 0;
+        for (int d = S.nd - 1; d >= 0; d--) {
+            const int64_t q = rem / S.count[d];
+            const int j = (int) (rem - q * S.count[d]);
+            rem = q;
+            soff += (int64_t) sidx[S.offset[d] + j] * S.sstride[d];
+            doff += (int64_t) didx[S.offset[d] + j] * S.dstride[d];
+        }
+        dst[doff] = src[soff];
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kThreads) diag_kernel(const T *__restrict__ src, T *dst, int64_t size) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < size; i += stride) {
+        dst[i] = src[i * size + i];
+    }
+}
+
+static void check_dims(const int32_t *dims, const int32_t *strides, int nd, int64_t len) {
+    int64_t acc = 0;
+    for (int i = 0; i < nd; i++) {
+        if (dims[i] < 0 || strides[i] < 0) {
+            throw std::runtime_error("Invalid dimensions and/or strides");
+        }
+        acc += (int64_t) (dims[i] - 1) * strides[i];
+    }
+    if (acc != len - 1) {
+        throw std::runtime_error("Invalid dimensions and/or strides");
+    }
+}
+
+static thread_local Scratch t_idx;
+
+struct ComplexPair {  // a complex element moved as two doubles (no 16-byte alignment requirement)
+    double re, im;
+};
+
+}  // namespace sstc
+
+using namespace sstc;
+
+extern "C" {
+
+int sstc_map_dev(int elem_bytes, const int32_t *bounds, int nbounds, const void *src, int64_t nsrc, const int32_t *sD,
+        const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd, void *stream) {
+    return guarded([&] {
+        cudaStream_t s = as_stream(stream);
+        if (elem_bytes != 4 && elem_bytes != 8) {
+            throw std::runtime_error("Invalid array types");  // NativeArrayKernel.cpp:134
+        }
+        if (!bounds || !sD || !sS || !dD || !dS || nd < 0 || nsrc < 0 || ndst < 0 || (nsrc > 0 && !src) ||
+                (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (nbounds != 3 * nd) {
+            throw std::runtime_error("Invalid arguments");  // MappingOpsMap.cpp:52-58
+        }
+        if (nd > kMaxDims) {
+            throw std::runtime_error("Too many dimensions for the CUDA provider");
+        }
+        check_dims(sD, sS, nd, nsrc);
+        check_dims(dD, dS, nd, ndst);
+        MapSpec M;
+        M.nd = nd;
+        M.total = 1;
+        for (int d = 0; d < nd; d++) {
+            if (bounds[3 * d + 2] < 0) {
+                throw std::runtime_error("Invalid mapping parameters");
+            }
+        }
+        if (nsrc == 0 || ndst == 0) {
+            return;
+        }
+        for (int d = 0; d < nd; d++) {
+            int32_t size = bounds[3 * d + 2];
+            const int32_t sdim = sD[d], ddim = dD[d];
+            int64_t s0 = bounds[3 * d], d0 = bounds[3 * d + 1];
+            // A map extent larger than the destination dimension rewrites destination indices; the reference
+            // copies in ascending order, so the LAST write wins: keep only the last `ddim` steps.
+            if (size > ddim) {
+                s0 += size - ddim;
+                d0 += size - ddim;
+                size = ddim;
+            }
+            M.size[d] = size;
+            M.sdim[d] = sdim;
+            M.ddim[d] = ddim;
+            M.sstart[d] = (int32_t) (((s0 % sdim) + sdim) % sdim);
+            M.dstart[d] = (int32_t) (((d0 % ddim) + ddim) % ddim);
+            M.sstride[d] = sS[d];
+            M.dstride[d] = dS[d];
+            M.total *= size;
+        }
+        if (M.total == 0) {
+            return;
+        }
+        const int grid = stream_grid(M.total);
+        if (elem_bytes == 8) {
+            map_kernel<double><<<grid, kThreads, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst), M);
+        } else {
+            map_kernel<int32_t><<<grid, kThreads, 0, s>>>(static_cast<const int32_t *>(src), static_cast<int32_t *>(dst), M);
+        }
+        check_launch("map_kernel");
+    });
+}
+
+int sstc_slice_dev(int elem_bytes, const int32_t *slices, int nslices3, const void *src, int64_t nsrc,
+        const int32_t *sD, const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd,
+        void *stream) {
+    return guarded([&] {
+        cudaStream_t s = as_stream(stream);
+        if (elem_bytes != 4 && elem_bytes != 8) {
+            throw std::runtime_error("Invalid array types");
+        }
+        if (!sD || !sS || !dD || !dS || nd < 0 || nsrc < 0 || ndst < 0 || (nslices3 > 0 && !slices) || nslices3 < 0 ||
+                (nsrc > 0 && !src) || (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (nslices3 % 3 != 0) {
+            throw std::runtime_error("Invalid arguments");  // MappingOpsSlice.cpp:52-58
+        }
+        if (nd > kMaxDims) {
+            throw std::runtime_error("Too many dimensions for the CUDA provider");
+        }
+        check_dims(sD, sS, nd, nsrc);
+        check_dims(dD, dS, nd, ndst);
+        const int n = nslices3 / 3;
+        for (int i = 0; i < n; i++) {
+            const int si = slices[3 * i], di = slices[3 * i + 1], dim = slices[3 * i + 2];
+            if (!(dim >= 0 && dim < nd)) {
+                throw std::runtime_error("Invalid dimension");
+            }
+            if (!(si >= 0 && si < sD[dim]) || !(di >= 0 && di < dD[dim])) {
+                throw std::runtime_error("Invalid index");
+            }
+        }
+        // per-dimension (src, dst) lists in specification order; a destination index named twice keeps its
+        // LAST source (sequential last-write-wins in the reference)
+        std::vector<std::vector<std::pair<int32_t, int32_t>>> per((size_t) nd);
+        for (int i = 0; i < n; i++) {
+            per[(size_t) slices[3 * i + 2]].push_back({slices[3 * i], slices[3 * i + 1]});
+        }
+        SliceSpec S;
+        S.nd = nd;
+        S.total = 1;
+        std::vector<int32_t> sidx, didx;
+        for (int d = 0; d < nd; d++) {
+            std::vector<std::pair<int32_t, int32_t>> kept;
+            std::vector<char> seen((size_t) std::max(dD[d], 1), 0);
+            for (int i = (int) per[(size_t) d].size() - 1; i >= 0; i--) {
+                const auto &pr = per[(size_t) d][(size_t) i];
+                if (!seen[(size_t) pr.second]) {
+                    seen[(size_t) pr.second] = 1;
+                    kept.push_back(pr);
+                }
+            }
+            std::reverse(kept.begin(), kept.end());
+            // total uses the reference's count (product of per-dimension list lengths) for the empty test
+            S.count[d] = (int32_t) kept.size();
+            S.offset[d] = (int32_t) sidx.size();
+            S.sstride[d] = sS[d];
+            S.dstride[d] = dS[d];
+            S.total *= (int64_t) kept.size();
+            for (const auto &pr : kept) {
+                sidx.push_back(pr.first);
+                didx.push_back(pr.second);
+            }
+        }
+        if (S.total == 0) {
+            return;
+        }
+        const size_t nidx = sidx.size();
+        int32_t *d_tab = static_cast<int32_t *>(t_idx.get((int64_t) (2 * nidx + 2) * 4));
+        SSTC_CUDA(cudaMemcpyAsync(d_tab, sidx.data(), nidx * 4, cudaMemcpyHostToDevice, s));
+        SSTC_CUDA(cudaMemcpyAsync(d_tab + nidx, didx.data(), nidx * 4, cudaMemcpyHostToDevice, s));
+        SSTC_CUDA(cudaStreamSynchronize(s));  // the pageable host vectors die with this scope
+        const int grid = stream_grid(S.total);
+        if (elem_bytes == 8) {
+            slice_kernel<double><<<grid, kThreads, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst), S,
+                    d_tab, d_tab + nidx);
+        } else {
+            slice_kernel<int32_t><<<grid, kThreads, 0, s>>>(static_cast<const int32_t *>(src), static_cast<int32_t *>(dst),
+                    S, d_tab, d_tab + nidx);
+        }
+        check_launch("slice_kernel");
+    });
+}
+
+int sstc_diag_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex, void *stream) {
+    return guarded([&] {
+        cudaStream_t s = as_stream(stream);
+        const int64_t f = complex ? 2 : 1;
+        if (size < 0 || nsrc != f * size * (int64_t) size || ndst != f * size) {
+            throw std::runtime_error("Invalid array lengths");  // MatrixOps.cpp:128-130
+        }
+        if ((nsrc > 0 && !src) || (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (size == 0) {
+            return;
+        }
+        const int grid = stream_grid(size);
+        if (complex) {
+            diag_kernel<ComplexPair><<<grid, kThreads, 0, s>>>(reinterpret_cast<const ComplexPair *>(src),
+                    reinterpret_cast<ComplexPair *>(dst), size);
+        } else {
+            diag_kernel<double><<<grid, kThreads, 0, s>>>(src, dst, size);
+        }
+        check_launch("diag_kernel");
+    });
+}
+
+}  // extern "C"
