@@ -231,12 +231,15 @@ def run_ours(args):
         parallelism = "1 GPU"
     else:
         from shared_b200.sharded import SlabFft3d
-        slab = SlabFft3d(DIMS, exchange=args.exchange, device=local)
+        slab = SlabFft3d(DIMS, exchange=args.exchange, device=local, groups=args.groups,
+                         exchange_ctas=args.exchange_ctas)
+        if args.exchange == "pipe" and not args.no_graph:
+            slab.capture(x)
 
         def step():
             slab.forward(x)
 
-        launches_per_step = slab.launches_per_forward()
+        launches_per_step = None  # counted below from the library's launch counter
         parallelism = "slab x%d over d0, %s exchange over NVLink" % (world, args.exchange)
 
     for _ in range(W):
@@ -370,10 +373,14 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--exchange", choices=["p2p", "collective"], default="p2p")
+    ap.add_argument("--exchange", choices=["pipe", "p2p", "collective"], default="pipe")
+    ap.add_argument("--exchange-ctas", type=int, default=None, dest="exchange_ctas",
+                    help="cap on the exchange pass's grid (0 = one CTA per tile)")
+    ap.add_argument("--groups", type=int, default=None, help="pipeline groups of the pipe exchange")
     ap.add_argument("--transposed-passes", type=int, default=None, dest="transposed_passes",
                     help="plan hint: -1 auto (default), 0 never, 1 always")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", dest="no_graph", help="issue the pipe schedule eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -108,6 +108,24 @@ int sstc_fft_axis_blocked_dev(void *const *d_in_blocks, int n_in, int64_t in_pit
         int n_out, int64_t out_pitch, int64_t outer, int32_t len, int64_t inner, int inverse, double scale,
         void *stream);
 
+/* Contiguous-axis pass with a line scatter. The input is (planes, plane_lines, len); the lines of a plane are
+ * cut into `nblocks` equal blocks. The call transforms lines [first, first + group) of every block of every
+ * plane and stores line yl of block q of plane xl at d_out_blocks[q] + (xl*(plane_lines/nblocks) + yl)*len
+ * (complex elements): whole lines per destination. This is the exchange pass of the pipelined slab transform:
+ * issued group by group, so the next axis can start on a group while later groups are still in flight.
+ * max_ctas > 0 caps the grid (the CTAs then loop over the tiles), leaving SM capacity for a concurrent pass. */
+int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes,
+        int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
+        void *stream);
+
+/* Cross-GPU barrier kernel (one process per GPU): d_flag_arrays[r] is rank r's array of 8 uint64 epoch slots,
+ * mapped by every rank (sstc_ipc_*) and zero-initialised (at least 9 slots: slot 8 is the rank's own call
+ * counter); `epoch` must increase with every call, or be 0 to let the kernel count calls itself (for use inside
+ * CUDA graphs). Stream-ordered:
+ * peer stores issued by earlier kernels on `stream` are complete before the flag is published, and kernels
+ * after it start only when every rank has published `epoch`. */
+int sstc_peer_barrier_dev(void *const *d_flag_arrays, int nranks, int rank, uint64_t epoch, void *stream);
+
 /* Cross-process device-memory sharing for the one-process-per-GPU layout (cudaIpc*): export a 64-byte
  * handle for a buffer from sstc_malloc, open a peer's handle, close it. */
 #define SSTC_IPC_HANDLE_BYTES 64

@@ -53,6 +53,14 @@ struct FftPassArgs {
     int64_t in_blk_pitch;
     double2 *blk[8];
     const double2 *in_blk[8];
+    // Line scatter (CONTIG c2c only; ls_group == 0 = off): the input is (planes, ls_plane_lines, L) and the
+    // lines of a plane are cut into ls_nblk blocks of ls_block_lines; this launch transforms lines
+    // [ls_first, ls_first + ls_group) of every block of every plane and stores line yl of block q of plane xl
+    // at blk[q] + (xl*ls_block_lines + yl)*L -- whole 16*L-byte lines per destination, which is what lets
+    // the exchange pass of the slab transform run in groups that the next pass can start consuming.
+    int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines;
+    int64_t ntiles;      // tiles in this launch (set by the launcher); the grid may be smaller
+    int64_t grid_limit;  // 0 = one CTA per tile
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -202,12 +210,11 @@ struct Pow2Stages<L, C, STRIDED, L> {
     __device__ __forceinline__ static void run(double2 (&)[8], int, int, double2 *, const double2 *) {}
 };
 
+// One tile (C lines of length L) of one pass; `blk` is the tile number.
 template <int L, int C, bool STRIDED>
-__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS)
-fft_pow2_kernel(const FftPassArgs a) {
+__device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_t blk, double2 *sm) {
     using Tile = Pow2Tile<L, C, STRIDED>;
     constexpr int T = Tile::T;
-    extern __shared__ double2 sm[];
 
     const int tid = threadIdx.x;
     int c, t;
@@ -219,26 +226,37 @@ fft_pow2_kernel(const FftPassArgs a) {
         c = tid / T;
     }
 
-    // Locate the tile. STRIDED: blockIdx.x -> (plane o, column tile); CONTIG: blockIdx.x -> C lines.
+    // Locate the tile. STRIDED: blk -> (plane o, column tile); CONTIG: blk -> C lines.
     bool active;
     int64_t in_base, out_base, in_ks, out_ks;
     int64_t line = 0;  // CONTIG line number (for r2c / c2r addressing)
     int64_t o = 0, i = 0;
+    double2 *out_line = nullptr;  // CONTIG line scatter destination
     if (STRIDED) {
         const int64_t tiles_per_plane = (a.inner + C - 1) / C;
-        o = blockIdx.x / tiles_per_plane;
-        i = (blockIdx.x - o * tiles_per_plane) * C + c;
+        o = blk / tiles_per_plane;
+        i = (blk - o * tiles_per_plane) * C + c;
         active = i < a.inner;
         in_base = o * a.in_plane + i;
         out_base = o * a.out_plane + i;
         in_ks = a.in_kstride;
         out_ks = a.out_kstride;
     } else {
-        line = (int64_t) blockIdx.x * C + c;
+        line = blk * C + c;
         active = line < a.outer;
         in_base = line * a.in_plane;
         out_base = line * a.out_plane;
         in_ks = out_ks = 1;
+        if (a.ls_group > 0) {
+            // line scatter: this launch covers, for every plane xl and every destination block q, the lines
+            // [ls_first, ls_first + ls_group) of that block; a whole line goes to one destination.
+            const int64_t yq = line % a.ls_group, t1 = line / a.ls_group;
+            const int q = (int) (t1 % a.ls_nblk);
+            const int64_t xl = t1 / a.ls_nblk;
+            const int64_t yl = a.ls_first + yq;
+            in_base = (xl * a.ls_plane_lines + (int64_t) q * a.ls_block_lines + yl) * L;
+            out_line = a.blk[q] + (xl * a.ls_block_lines + yl) * L;
+        }
     }
 
     double2 v[8];
@@ -303,6 +321,12 @@ fft_pow2_kernel(const FftPassArgs a) {
             const int pk = p - q * a.ksplit;
             a.blk[q][(o * a.ksplit + pk) * a.blk_pitch + i] = z;
         }
+    } else if (!STRIDED && a.ls_group > 0) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+            out_line[t + m * T] = z;
+        }
     } else if (a.mode == MODE_C2C) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -323,6 +347,20 @@ fft_pow2_kernel(const FftPassArgs a) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             rout[t + m * T] = (a.inverse ? v[m].y : v[m].x) * s;
+        }
+    }
+}
+
+// Grid = one CTA per tile normally; a smaller grid makes the CTAs loop over the tiles, which is how the
+// NVLink-bound exchange pass is confined to a fraction of every SM so that the next pass can run beside it.
+template <int L, int C, bool STRIDED>
+__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS)
+fft_pow2_kernel(const FftPassArgs a) {
+    extern __shared__ double2 sm[];
+    for (int64_t blk = blockIdx.x; blk < a.ntiles; blk += gridDim.x) {
+        fft_pow2_tile<L, C, STRIDED>(a, blk, sm);
+        if (blk + gridDim.x < a.ntiles) {
+            __syncthreads();
         }
     }
 }

@@ -8,6 +8,7 @@
 // loop (FftOps.java:65-84) visits the same axes, rotating the layout each time instead.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
@@ -117,7 +118,12 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
     if (grid > kMaxGrid) {
         throw std::runtime_error("FFT batch too large for one launch");
     }
-    fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
+    FftPassArgs b = a;
+    b.ntiles = grid;
+    if (a.grid_limit > 0 && a.grid_limit < grid) {
+        grid = a.grid_limit;
+    }
+    fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(b);
     check_launch("fft_pow2_kernel");
 }
 
@@ -202,6 +208,8 @@ static void launch_generic(const FftPassArgs &a, int L, cudaStream_t stream) {
     check_launch("fft_generic_kernel");
 }
 
+static void dispatch_axis(const FftPassArgs &a, int L, bool strided, cudaStream_t stream);
+
 // Optional blocked addressing of one side of a pass (see FftPassArgs).
 struct Blocks {
     int n = 0;
@@ -237,6 +245,8 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.mode = mode;
     a.inverse = inverse;
     a.ksplit = a.in_ksplit = 0;
+    a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = 0;
+    a.ntiles = a.grid_limit = 0;
     a.blk_pitch = a.in_blk_pitch = inner;
     for (int q = 0; q < 8; q++) {
         a.blk[q] = nullptr;
@@ -265,6 +275,10 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     }
     // blocked addressing lives in the STRIDED kernels; inner == 1 is routed there as a 1-column plane
     const bool strided = inner > 1 || bin.n > 0 || bout.n > 0 || layout;
+    dispatch_axis(a, L, strided, stream);
+}
+
+static void dispatch_axis(const FftPassArgs &a, int L, bool strided, cudaStream_t stream) {
     switch (L) {
     case 8: launch_pow2_L<8>(a, strided, stream); break;
     case 16: launch_pow2_L<16>(a, strided, stream); break;
@@ -573,6 +587,45 @@ int sstc_fft_axis_strided_dev(const double *d_in, double *d_out, int64_t outer, 
         const int64_t layout[4] = {in_plane, in_kstride, out_plane, out_kstride};
         launch_axis(d_in, d_out, outer, len, inner, MODE_C2C, inverse ? 1 : 0, scale, as_stream(stream), Blocks(),
                 Blocks(), layout);
+    });
+}
+
+int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes,
+        int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
+        void *stream) {
+    return guarded([&] {
+        if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || planes < 0 || plane_lines <= 0 || len <= 0 ||
+                plane_lines % nblocks != 0 || first < 0 || group <= 0 || first + group > plane_lines / nblocks) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (!(len >= 8 && len <= 4096 && (len & (len - 1)) == 0)) {
+            throw std::runtime_error("line scatter needs a power-of-two length between 8 and 4096");
+        }
+        if (planes == 0) {
+            return;
+        }
+        FftPassArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = reinterpret_cast<const double2 *>(d_in);
+        a.tw = pow2_twiddles_for(len);
+        a.outer = planes * nblocks * (int64_t) group;  // lines in this launch
+        a.inner = 1;
+        a.in_plane = a.out_plane = len;
+        a.in_kstride = a.out_kstride = 1;
+        a.scale = scale;
+        a.mode = MODE_C2C;
+        a.inverse = inverse ? 1 : 0;
+        a.blk_pitch = a.in_blk_pitch = 1;
+        for (int q = 0; q < nblocks; q++) {
+            a.blk[q] = static_cast<double2 *>(d_out_blocks[q]);
+        }
+        a.ls_group = group;
+        a.ls_nblk = nblocks;
+        a.ls_first = first;
+        a.ls_block_lines = plane_lines / nblocks;
+        a.ls_plane_lines = plane_lines;
+        a.grid_limit = max_ctas > 0 ? max_ctas : 0;
+        dispatch_axis(a, len, false, as_stream(stream));
     });
 }
 

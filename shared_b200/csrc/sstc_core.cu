@@ -28,6 +28,45 @@ Scratch::~Scratch() {
     // Process teardown: the CUDA context may already be gone; leak rather than call into a dead runtime.
 }
 
+// Cross-GPU barrier for the one-process-per-GPU slab transform: every rank owns an array of 8 epoch slots that
+// all ranks map (CUDA IPC). Rank r publishes `epoch` into slot r of every rank's array, then waits until its
+// own array shows `epoch` from everyone. Launched after the kernel whose peer stores it fences, on the same
+// stream, so those stores are complete before the flag is written. One kernel per rank, each on its own GPU,
+// so the waiting ranks are always co-resident. A bounded spin (~4 s) turns a missing peer into stale data the
+// parity checks catch rather than a hung device.
+struct PeerFlags {
+    unsigned long long *ptr[8];
+};
+
+__global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (epoch == 0) {
+        // self-counting mode (CUDA-graph friendly: no per-launch argument changes): slot 8 of the rank's own
+        // array counts this rank's barriers; every rank issues the same sequence, so the counts agree.
+        __shared__ unsigned long long next;
+        if (r == 0) {
+            next = ++f.ptr[rank][8];
+        }
+        __syncthreads();
+        epoch = next;
+    }
+    if (r >= nranks) {
+        return;
+    }
+    __threadfence_system();
+    volatile unsigned long long *remote = f.ptr[r] + rank;
+    *remote = epoch;
+    __threadfence_system();
+    volatile unsigned long long *local = f.ptr[rank] + r;
+    const long long start = clock64();
+    while (*local < epoch) {
+        if (clock64() - start > 8000000000LL) {
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace sstc
 
 using namespace sstc;
@@ -155,6 +194,20 @@ int sstc_ipc_close(void *dptr) {
         if (dptr) {
             SSTC_CUDA(cudaIpcCloseMemHandle(dptr));
         }
+    });
+}
+
+int sstc_peer_barrier_dev(void *const *d_flag_arrays, int nranks, int rank, uint64_t epoch, void *stream) {
+    return guarded([&] {
+        if (!d_flag_arrays || nranks <= 0 || nranks > 8 || rank < 0 || rank >= nranks) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        PeerFlags f;
+        for (int r = 0; r < 8; r++) {
+            f.ptr[r] = r < nranks ? static_cast<unsigned long long *>(d_flag_arrays[r]) : nullptr;
+        }
+        peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, nranks, rank, (unsigned long long) epoch);
+        check_launch("peer_barrier_kernel");
     });
 }
 

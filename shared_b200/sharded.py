@@ -11,9 +11,14 @@ result locally but scatters block q of the y axis straight to rank q (sstc_fft_a
 transfer and unpack are part of the FFT kernel's store; the x pass then runs on the received
 (d0, d1/P, d2) array. inverse(): transposed -> natural, mirrored (x pass scatters x blocks to their owners).
 
-Two exchange modes:
-    "p2p"         destination blocks are the peers' receive buffers, mapped through CUDA IPC; the kernel
-                  stores over NVLink. One cross-rank barrier per transform (receive buffers are double-buffered).
+Three exchange modes:
+    "pipe"        (default on GPUs) the y pass runs first, locally; the z pass is the exchange pass: it stores whole
+                  z lines straight into the owner's receive buffer over NVLink (CUDA IPC mapping), in G groups of
+                  y indices. After each group a flag barrier kernel runs on a side stream and the x pass of that
+                  group's columns starts on a third stream, so the x pass (HBM-bound) overlaps the remaining
+                  exchange (NVLink-bound). forward() only.
+    "p2p"         z pass, then the y pass scatters 128-byte row segments into the peers' receive buffers; one
+                  cross-rank barrier, then the x pass. Also implements inverse().
     "collective"  destination blocks are a local send buffer; torch.distributed all_to_all_single moves them
                   (NCCL on GPUs, gloo in the CPU tests). Baseline and fallback for the host-logic tests.
 
@@ -57,6 +62,27 @@ class CudaEngine:
         _lib.check(_lib.lib().sstc_fft_axis_blocked_dev(
             sp, len(src_blocks), int(src_pitch), dp, len(dst_blocks), int(dst_pitch), int(outer), int(length),
             int(inner), int(bool(inverse)), float(scale), ctypes.c_void_p(self._stream())))
+
+
+    def axis_strided(self, src, dst, outer, length, inner, in_plane, in_kstride, out_plane, out_kstride,
+                     inverse=False, scale=1.0):
+        _lib.check(_lib.lib().sstc_fft_axis_strided_dev(
+            ctypes.c_void_p(self._ptr(src)), ctypes.c_void_p(self._ptr(dst)), int(outer), int(length), int(inner),
+            int(in_plane), int(in_kstride), int(out_plane), int(out_kstride), int(bool(inverse)), float(scale),
+            ctypes.c_void_p(self._stream())))
+
+    def lines_scatter(self, src, dst_blocks, planes, plane_lines, length, first, group, inverse=False, scale=1.0,
+                      max_ctas=0):
+        dp = (ctypes.c_void_p * len(dst_blocks))(*[self._ptr(b) for b in dst_blocks])
+        _lib.check(_lib.lib().sstc_fft_lines_scatter_dev(
+            ctypes.c_void_p(self._ptr(src)), dp, len(dst_blocks), int(planes), int(plane_lines), int(length),
+            int(first), int(group), int(bool(inverse)), float(scale), int(max_ctas),
+            ctypes.c_void_p(self._stream())))
+
+    def peer_barrier(self, flag_ptrs, rank, epoch):
+        fp = (ctypes.c_void_p * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
+        _lib.check(_lib.lib().sstc_peer_barrier_dev(fp, len(flag_ptrs), int(rank), ctypes.c_uint64(int(epoch)),
+                                                    ctypes.c_void_p(self._stream())))
 
 
 class _DeviceArray:
@@ -111,7 +137,8 @@ def block_ptrs(base, n_blocks, block_elems):
 class SlabFft3d:
     """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
 
-    def __init__(self, dims, group=None, exchange="p2p", engine=None, device=None):
+    def __init__(self, dims, group=None, exchange="pipe", engine=None, device=None, groups=None,
+                 exchange_ctas=None):
         if len(dims) != 3:
             raise ValueError("SlabFft3d needs three dimensions")
         self.group = group
@@ -128,15 +155,27 @@ class SlabFft3d:
         self.engine = engine if engine is not None else CudaEngine(device if device is not None else 0)
         self.work = self.engine.empty(self.n_local)
         self._step = 0
-        if exchange == "p2p":
+        if exchange in ("p2p", "pipe"):
             dev = self.engine.device
             self.peer = [PeerBuffer(self.n_local, dev, group) for _ in range(2)]
             self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            self.groups = next(g for g in (groups or 4, 4, 2, 1) if self.y_loc % g == 0)
+            # measured on 8 B200 (512^3): one exchange CTA per SM keeps NVLink busy (74 do not) and leaves room for the
+            # x pass to run beside it; an uncapped grid starves the x pass and loses the overlap (0.55 vs 0.51 ms)
+            self.exchange_ctas = (torch.cuda.get_device_properties(dev).multi_processor_count
+                                  if exchange_ctas is None else int(exchange_ctas))
+            self.flags = PeerBuffer(16, dev, group)  # 8 uint64 epoch slots per rank (+ padding)
+            self.flags.tensor.zero_()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group)
+            self._epoch = 0
+            self.s_bar = torch.cuda.Stream(dev, priority=-1)
+            self.s_x = torch.cuda.Stream(dev, priority=-1)  # its CTAs must win SM slots from the pending exchange CTAs
         elif exchange == "collective":
             self.send = self.engine.empty(self.n_local)
             self.recv = self.engine.empty(self.n_local)
         else:
-            raise ValueError("exchange must be 'p2p' or 'collective'")
+            raise ValueError("exchange must be 'pipe', 'p2p' or 'collective'")
 
     # -- cross-rank ordering ----------------------------------------------------------------------------
     def _barrier(self):
@@ -145,9 +184,64 @@ class SlabFft3d:
         dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
 
     # -- transforms ---------------------------------------------------------------------------------------
+    def _forward_pipe(self, x):
+        e, p = self.engine, self.world
+        dev = e.device
+        cur = torch.cuda.current_stream(dev)
+        e.axis(x, self.work, self.x_loc, self.d1, self.d2)                                       # y, local
+        buf = self.peer[self._step % 2]
+        self._step += 1
+        dst = [buf.ptrs[q] + self.rank * self.block * 16 for q in range(p)]
+        yg = self.y_loc // self.groups
+        cols = yg * self.d2                      # columns of the received (d0, y_loc*d2) array per group
+        kstride = self.y_loc * self.d2
+        for g in range(self.groups):
+            e.lines_scatter(self.work, dst, self.x_loc, self.d1, self.d2, g * yg, yg,
+                            max_ctas=self.exchange_ctas)                                          # z + transpose
+            sent = cur.record_event()
+            self.s_bar.wait_event(sent)
+            with torch.cuda.stream(self.s_bar):
+                e.peer_barrier(self.flags.ptrs, self.rank, 0)  # self-counting epochs: graph-capturable
+                arrived = self.s_bar.record_event()
+            self.s_x.wait_event(arrived)
+            with torch.cuda.stream(self.s_x):
+                ptr = buf.local_ptr + g * cols * 16
+                e.axis_strided(ptr, ptr, 1, self.d0, cols, 0, kstride, 0, kstride)               # x on this group
+        cur.wait_stream(self.s_x)
+        return buf.tensor
+
+    def capture(self, x):
+        """Record the pipelined forward schedule for input buffer `x` into two CUDA graphs (one per receive
+        buffer) so that a step costs one graph launch instead of ~3G+1 Python-issued launches."""
+        if self.exchange != "pipe":
+            raise ValueError("capture() is for the 'pipe' exchange")
+        dev = self.engine.device
+        for _ in range(2):  # warm up both parities eagerly (first-use attribute calls are not capturable)
+            self._forward_pipe(x)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)
+        self._graphs, self._graph_out, self._graph_in = [], [], x.data_ptr()
+        side = torch.cuda.Stream(dev)
+        for parity in range(2):
+            assert self._step % 2 == parity
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+                out = self._forward_pipe(x)
+            self._graphs.append(g)
+            self._graph_out.append(out)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)
+
     def forward(self, x):
         """x: this rank's natural slab, (n_local, 2) float64. Returns this rank's transposed slab (a view
         of an internal buffer, valid until the next-but-one call)."""
+        if self.exchange == "pipe":
+            if getattr(self, "_graphs", None) and x.data_ptr() == self._graph_in:
+                parity = self._step % 2
+                self._step += 1
+                self._graphs[parity].replay()
+                return self._graph_out[parity]
+            return self._forward_pipe(x)
         e, p = self.engine, self.world
         e.axis(x, self.work, self.x_loc * self.d1, self.d2, 1)                                   # z
         if self.exchange == "p2p":
@@ -168,7 +262,7 @@ class SlabFft3d:
         """y: this rank's transposed slab. Returns this rank's natural slab of ifft (scaled by 1/N)."""
         e, p = self.engine, self.world
         row = self.d1 * self.d2  # one x row of a natural slab
-        if self.exchange == "p2p":
+        if self.exchange in ("p2p", "pipe"):
             buf = self.peer[self._step % 2]
             self._step += 1
             # x block q -> rank q, landing at columns [rank*y_loc*d2, ...) of each of its x rows
@@ -192,8 +286,8 @@ class SlabFft3d:
         return 3
 
     def close(self):
-        if self.exchange == "p2p":
-            for b in self.peer:
+        if self.exchange in ("p2p", "pipe"):
+            for b in self.peer + [self.flags]:
                 b.close()
 
 

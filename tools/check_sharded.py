@@ -24,7 +24,7 @@ for dims in ([64, 64, 64], [128, 64, 32], [512, 512, 512]):
     plan.execute(full.data_ptr(), ref.data_ptr(), torch.cuda.current_stream().cuda_stream)
     n_loc = n // world
     mine = full[rank * n_loc:(rank + 1) * n_loc].clone()
-    for mode in ("collective", "p2p"):
+    for mode in ("collective", "p2p", "pipe"):
         slab = SlabFft3d(dims, exchange=mode, device=local)
         for it in range(3):  # exercise the double-buffered receive side
             out = slab.forward(mine)
