@@ -61,6 +61,7 @@ struct FftPassArgs {
     int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines;
     int64_t ntiles;      // tiles in this launch (set by the launcher); the grid may be smaller
     int64_t grid_limit;  // 0 = one CTA per tile
+    int reverse;         // process the tiles in descending order
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -146,6 +147,8 @@ struct Pow2Tile {
     static constexpr bool PADDED = !STRIDED || (C < 8);
     static constexpr int LINE = PADDED ? fft_pad(L) : L;  // smem elements per line
     static constexpr int SMEM_BYTES = (L > 8) ? LINE * C * 16 : 0;
+    // keep 1024 threads resident per SM (<= 64 registers per thread): the passes are latency-bound otherwise
+    static constexpr int MIN_CTAS = (1024 / THREADS) < 1 ? 1 : (1024 / THREADS) > 8 ? 8 : (1024 / THREADS);
 };
 
 // One Stockham stage with Ns = NS already-combined points, followed (if not last) by the smem exchange and
@@ -210,8 +213,10 @@ struct Pow2Stages<L, C, STRIDED, L> {
     __device__ __forceinline__ static void run(double2 (&)[8], int, int, double2 *, const double2 *) {}
 };
 
-// One tile (C lines of length L) of one pass; `blk` is the tile number.
-template <int L, int C, bool STRIDED>
+// One tile (C lines of length L) of one pass; `blk` is the tile number. EXT = false is the lean hot path
+// (natural layout); EXT = true adds explicit point strides, blocked addressing and the line scatter, which
+// cost registers the hot path cannot spare at 1024 resident threads per SM.
+template <int L, int C, bool STRIDED, bool EXT>
 __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_t blk, double2 *sm) {
     using Tile = Pow2Tile<L, C, STRIDED>;
     constexpr int T = Tile::T;
@@ -239,15 +244,15 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
         active = i < a.inner;
         in_base = o * a.in_plane + i;
         out_base = o * a.out_plane + i;
-        in_ks = a.in_kstride;
-        out_ks = a.out_kstride;
+        in_ks = EXT ? a.in_kstride : a.inner;
+        out_ks = EXT ? a.out_kstride : a.inner;
     } else {
         line = blk * C + c;
         active = line < a.outer;
         in_base = line * a.in_plane;
         out_base = line * a.out_plane;
         in_ks = out_ks = 1;
-        if (a.ls_group > 0) {
+        if (EXT && a.ls_group > 0) {
             // line scatter: this launch covers, for every plane xl and every destination block q, the lines
             // [ls_first, ls_first + ls_group) of that block; a whole line goes to one destination.
             const int64_t yq = line % a.ls_group, t1 = line / a.ls_group;
@@ -261,7 +266,7 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
 
     double2 v[8];
     if (active) {
-        if (STRIDED && a.in_ksplit > 0) {
+        if (EXT && STRIDED && a.in_ksplit > 0) {
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 const int p = t + m * T;
@@ -312,7 +317,7 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
         return;
     }
     const double s = a.scale;
-    if (STRIDED && a.ksplit > 0) {
+    if (EXT && STRIDED && a.ksplit > 0) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
@@ -321,7 +326,7 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
             const int pk = p - q * a.ksplit;
             a.blk[q][(o * a.ksplit + pk) * a.blk_pitch + i] = z;
         }
-    } else if (!STRIDED && a.ls_group > 0) {
+    } else if (EXT && !STRIDED && a.ls_group > 0) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
@@ -354,15 +359,24 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
 // Grid = one CTA per tile normally; a smaller grid makes the CTAs loop over the tiles, which is how the
 // NVLink-bound exchange pass is confined to a fraction of every SM so that the next pass can run beside it.
 template <int L, int C, bool STRIDED>
-__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS)
-fft_pow2_kernel(const FftPassArgs a) {
+__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS, Pow2Tile<L, C, STRIDED>::MIN_CTAS)
+fft_pow2_ext_kernel(const FftPassArgs a) {
     extern __shared__ double2 sm[];
     for (int64_t blk = blockIdx.x; blk < a.ntiles; blk += gridDim.x) {
-        fft_pow2_tile<L, C, STRIDED>(a, blk, sm);
+        // reverse: walk the tiles from the end (the data the previous pass wrote last is still in L2)
+        fft_pow2_tile<L, C, STRIDED, true>(a, a.reverse ? a.ntiles - 1 - blk : blk, sm);
         if (blk + gridDim.x < a.ntiles) {
             __syncthreads();
         }
     }
+}
+
+// The hot path: one tile per CTA, natural layout.
+template <int L, int C, bool STRIDED>
+__global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS, Pow2Tile<L, C, STRIDED>::MIN_CTAS)
+fft_pow2_kernel(const FftPassArgs a) {
+    extern __shared__ double2 sm[];
+    fft_pow2_tile<L, C, STRIDED, false>(a, blockIdx.x, sm);
 }
 
 // ---------------------------------------------------------------------------------------------------------

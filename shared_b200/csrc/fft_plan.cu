@@ -113,18 +113,28 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
         std::call_once(once[dev & 15], [] {
             SSTC_CUDA(cudaFuncSetAttribute(fft_pow2_kernel<L, C, STRIDED>,
                     cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM_BYTES));
+            SSTC_CUDA(cudaFuncSetAttribute(fft_pow2_ext_kernel<L, C, STRIDED>,
+                    cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM_BYTES));
         });
     }
     if (grid > kMaxGrid) {
         throw std::runtime_error("FFT batch too large for one launch");
+    }
+    // anything beyond "one tile per CTA, natural layout" runs the extended kernel
+    const bool ext = a.ksplit > 0 || a.in_ksplit > 0 || a.ls_group > 0 || a.grid_limit > 0 || a.reverse ||
+            (STRIDED && (a.in_kstride != a.inner || a.out_kstride != a.inner));
+    if (!ext) {
+        fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
+        check_launch("fft_pow2_kernel");
+        return;
     }
     FftPassArgs b = a;
     b.ntiles = grid;
     if (a.grid_limit > 0 && a.grid_limit < grid) {
         grid = a.grid_limit;
     }
-    fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(b);
-    check_launch("fft_pow2_kernel");
+    fft_pow2_ext_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(b);
+    check_launch("fft_pow2_ext_kernel");
 }
 
 template <int L>
@@ -220,7 +230,7 @@ struct Blocks {
 // One pass over axis `L` of (outer, L, inner). For MODE_R2C / MODE_C2R, inner must be 1 and outer counts lines.
 static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse,
         double scale, cudaStream_t stream, const Blocks &bin = Blocks(), const Blocks &bout = Blocks(),
-        const int64_t *layout = nullptr) {
+        const int64_t *layout = nullptr, int reverse = 0) {
     if (outer <= 0 || inner <= 0 || L <= 0) {
         return;
     }
@@ -247,6 +257,7 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.ksplit = a.in_ksplit = 0;
     a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = 0;
     a.ntiles = a.grid_limit = 0;
+    a.reverse = reverse;
     a.blk_pitch = a.in_blk_pitch = inner;
     for (int q = 0; q < 8; q++) {
         a.blk[q] = nullptr;
@@ -317,6 +328,7 @@ struct sstc_fft_plan_s {
     void *workspace = nullptr;
     int64_t workspace_bytes = 0;
     int transposed_passes = -1;  // hint: -1 auto, 0 never, 1 whenever legal
+    int alternate_order = 0;     // hint: odd passes process their tiles in descending order (measured: no gain)
 };
 
 namespace sstc {
@@ -465,11 +477,14 @@ static void execute_plan(sstc_fft_plan_s &p, const double *d_in, double *d_out, 
     if (!d_in || !d_out) {
         throw std::runtime_error("Invalid arguments");
     }
+    int pass = 0;
     for (const Step &s : p.steps) {
         const void *src = s.src == 0 ? (const void *) d_in : s.src == 1 ? (const void *) d_out : p.workspace;
         void *dst = s.dst == 1 ? (void *) d_out : p.workspace;
+        // odd passes walk their tiles backwards: they begin on what the previous pass wrote last (L2-resident)
         launch_axis(src, dst, s.outer, s.axis_len, s.inner, s.mode, p.inverse, s.scale, stream, Blocks(), Blocks(),
-                s.layout[1] ? s.layout : nullptr);
+                s.layout[1] ? s.layout : nullptr, (pass & 1) && p.alternate_order);
+        pass++;
     }
 }
 
@@ -555,7 +570,9 @@ int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value) 
         if (!plan || !name) {
             throw std::runtime_error("Invalid arguments");
         }
-        if (std::string(name) == "transposed_passes") {
+        if (std::string(name) == "alternate_order") {
+            plan->alternate_order = value ? 1 : 0;
+        } else if (std::string(name) == "transposed_passes") {
             if (value < -1 || value > 1) {
                 throw std::runtime_error("Invalid hint value");
             }

@@ -1,5 +1,5 @@
 """Tuning sweep (run on the GPU box): per-pass and per-step CUDA-event times at 512^3 for the current
-SSTC_FFT512_* tile settings and both plan schedules."""
+SSTC_FFT512_* tile settings and the plan hints."""
 import json
 import os
 import sys
@@ -31,14 +31,14 @@ def ev(fn, reps=20):
 
 res = {"env": {k: v for k, v in os.environ.items() if k.startswith("SSTC_")}}
 res["z"] = ev(lambda: s.fft_axis(x.data_ptr(), y.data_ptr(), 512 * 512, 512, 1, False, 1.0, st))
-res["z_inplace"] = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), 512 * 512, 512, 1, False, 1.0, st))
 res["y"] = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), 512, 512, 512, False, 1.0, st))
 res["x"] = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), 1, 512, 512 * 512, False, 1.0, st))
 res["copy"] = ev(lambda: y.copy_(x))
 plan = s.FftPlan(s.FORWARD, dims)
-for tp in (0, 1):
-    plan.set_hint("transposed_passes", tp)
-    res["step_transposed%d" % tp] = ev(lambda: plan.execute(x.data_ptr(), y.data_ptr(), st))
+for hint, values in (("alternate_order", (0, 1)), ("transposed_passes", (1, 0))):
+    for v in values:
+        plan.set_hint(hint, v)
+        res["step_%s=%d" % (hint, v)] = ev(lambda: plan.execute(x.data_ptr(), y.data_ptr(), st), 50)
 xc = torch.view_as_complex(x).reshape(dims)
 res["cufft_torch"] = ev(lambda: torch.fft.fftn(xc), 10)
 print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in res.items()}))
