@@ -63,30 +63,16 @@ uint64_t next_rng_key();  // advances the library-global call counter (array_ele
 
 // Java Math.max / Math.min semantics (NaN wins, -0.0 < +0.0): ElementOps.java RE_MAX / RE_MIN go through
 // Math.max/min; the reference's C++ uses std::max/min, which differ only on NaN and signed zeros.
-__device__ inline double java_max(double a, double b) {
-    if (a != a) {
-        return a;
-    }
-    if (b != b) {
-        return b;
-    }
-    if (a == 0.0 && b == 0.0) {
-        return signbit(a) ? b : a;
-    }
-    return a > b ? a : b;
+// fmax/fmin (PTX max.f64 / min.f64) already order -0.0 below +0.0; they return the non-NaN operand, so the NaN
+// case is patched with selects (no branches: these sit in the inner loops of the MAX / MIN folds).
+__device__ __forceinline__ double java_max(double a, double b) {
+    const double r = fmax(a, b);
+    return (a != a) ? a : ((b != b) ? b : r);
 }
 
-__device__ inline double java_min(double a, double b) {
-    if (a != a) {
-        return a;
-    }
-    if (b != b) {
-        return b;
-    }
-    if (a == 0.0 && b == 0.0) {
-        return signbit(a) ? a : b;
-    }
-    return a < b ? a : b;
+__device__ __forceinline__ double java_min(double a, double b) {
+    const double r = fmin(a, b);
+    return (a != a) ? a : ((b != b) ? b : r);
 }
 
 }  // namespace sstc

@@ -294,38 +294,59 @@ __device__ __forceinline__ double rd_combine(double a, double b) {
 }
 
 // CTA per line, lanes along the line; rounds of blockDim points with a running carry.
+// Each thread scans kScanItems consecutive points in registers, the thread totals are scanned with shuffles
+// and one shared-memory hop per round of 256 * kScanItems points, and a running carry links the rounds.
+constexpr int kScanItems = 8;
+
 template <int OP>
 __global__ void __launch_bounds__(kThreads) scan_lines_block_kernel(const double *in, double *out, Lines L) {
     __shared__ double warp_tot[kThreads / 32];
     __shared__ double carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double ident = OP == RD_SUM ? 0.0 : 1.0;
     for (int64_t m = blockIdx.x; m < L.n_lines; m += gridDim.x) {
         int64_t ioff, ooff;
         line_base(L, m, ioff, ooff);
-        double carry = OP == RD_SUM ? 0.0 : 1.0;
-        for (int64_t base = 0; base < L.len; base += blockDim.x) {
-            const int64_t j = base + threadIdx.x;
-            double x = j < L.len ? in[ioff + j * L.ilstride] : (OP == RD_SUM ? 0.0 : 1.0);
+        double carry = ident;
+        for (int64_t base = 0; base < L.len; base += (int64_t) blockDim.x * kScanItems) {
+            const int64_t j0 = base + (int64_t) threadIdx.x * kScanItems;
+            double x[kScanItems];
+#pragma unroll
+            for (int e = 0; e < kScanItems; e++) {
+                x[e] = j0 + e < L.len ? in[ioff + (j0 + e) * L.ilstride] : ident;
+            }
+#pragma unroll
+            for (int e = 1; e < kScanItems; e++) {
+                x[e] = rd_combine<OP>(x[e - 1], x[e]);
+            }
+            double tot = x[kScanItems - 1];  // inclusive scan of the thread totals across the warp
             for (int off = 1; off < 32; off <<= 1) {
-                double y = __shfl_up_sync(0xffffffffu, x, off);
+                double y = __shfl_up_sync(0xffffffffu, tot, off);
                 if (lane >= off) {
-                    x = rd_combine<OP>(y, x);
+                    tot = rd_combine<OP>(y, tot);
                 }
             }
             if (lane == 31) {
-                warp_tot[warp] = x;
+                warp_tot[warp] = tot;
+            }
+            double excl = __shfl_up_sync(0xffffffffu, tot, 1);  // exclusive prefix within the warp
+            if (lane == 0) {
+                excl = ident;
             }
             __syncthreads();
             double pre = carry;
             for (int w = 0; w < warp; w++) {
                 pre = rd_combine<OP>(pre, warp_tot[w]);
             }
-            x = rd_combine<OP>(pre, x);
-            if (j < L.len) {
-                out[ooff + j * L.olstride] = x;
+            pre = rd_combine<OP>(pre, excl);
+#pragma unroll
+            for (int e = 0; e < kScanItems; e++) {
+                if (j0 + e < L.len) {
+                    out[ooff + (j0 + e) * L.olstride] = rd_combine<OP>(pre, x[e]);
+                }
             }
             if (threadIdx.x == blockDim.x - 1) {
-                carry_s = x;
+                carry_s = rd_combine<OP>(pre, x[kScanItems - 1]);
             }
             __syncthreads();
             carry = carry_s;

@@ -25,20 +25,77 @@ struct MapSpec {
     int64_t sstride[kMaxDims], dstride[kMaxDims];
 };
 
-template <class T>
+// I = uint32_t when the map has fewer than 2^31 elements (32-bit division is several times cheaper)
+template <class T, class I>
 __global__ void __launch_bounds__(kThreads) map_kernel(const T *__restrict__ src, T *dst, MapSpec M) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     for (int64_t m = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; m < M.total; m += stride) {
-        int64_t rem = m, soff = 0, doff = 0;
+        I rem = (I) m;
+        int64_t soff = 0, doff = 0;
         for (int d = M.nd - 1; d >= 0; d--) {
-            const int64_t q = rem / M.size[d];
-            const int j = (int) (rem - q * M.size[d]);
+            const I q = rem / (I) M.size[d];
+            const uint32_t j = (uint32_t) (rem - q * (I) M.size[d]);
             rem = q;
             // indices wrap modulo the dimension on both sides (MappingOps.java:237-249)
-            soff += (int64_t) ((M.sstart[d] + j) % M.sdim[d]) * M.sstride[d];
-            doff += (int64_t) ((M.dstart[d] + j) % M.ddim[d]) * M.dstride[d];
+            soff += (int64_t) (((uint32_t) M.sstart[d] + j) % (uint32_t) M.sdim[d]) * M.sstride[d];
+            doff += (int64_t) (((uint32_t) M.dstart[d] + j) % (uint32_t) M.ddim[d]) * M.dstride[d];
         }
         dst[doff] = src[soff];
+    }
+}
+
+// When the fastest-varying dimension differs between source and destination (transposes, reverseOrder), a
+// thread-per-element copy is uncoalesced on one side. This kernel moves 32 x 32 tiles over (A = the source's
+// fastest dimension, B = the destination's) through shared memory: loads run along A, stores along B.
+struct MapTileSpec {
+    int da, db;          // the two tiled dimensions
+    int32_t ta, tb;      // tiles along A and B
+    int64_t rest;        // product of the other extents
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) map_tile_kernel(const T *__restrict__ src, T *dst, MapSpec M, MapTileSpec S) {
+    __shared__ T tile[32][33];
+    const int64_t ntiles = (int64_t) S.ta * S.tb * S.rest;
+    for (int64_t blk = blockIdx.x; blk < ntiles; blk += gridDim.x) {
+        int64_t rem = blk;
+        const int ia = (int) (rem % S.ta);
+        rem /= S.ta;
+        const int ib = (int) (rem % S.tb);
+        rem /= S.tb;
+        int64_t soff = 0, doff = 0;
+        for (int d = M.nd - 1; d >= 0; d--) {
+            if (d == S.da || d == S.db) {
+                continue;
+            }
+            const int64_t q = rem / M.size[d];
+            const uint32_t j = (uint32_t) (rem - q * M.size[d]);
+            rem = q;
+            soff += (int64_t) (((uint32_t) M.sstart[d] + j) % (uint32_t) M.sdim[d]) * M.sstride[d];
+            doff += (int64_t) (((uint32_t) M.dstart[d] + j) % (uint32_t) M.ddim[d]) * M.dstride[d];
+        }
+        const int a0 = ia * 32, b0 = ib * 32;
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t ja = (uint32_t) (a0 + tx), jb = (uint32_t) (b0 + ty + 8 * r);
+            if (ja < (uint32_t) M.size[S.da] && jb < (uint32_t) M.size[S.db]) {
+                tile[ty + 8 * r][tx] = src[soff +
+                        (int64_t) (((uint32_t) M.sstart[S.da] + ja) % (uint32_t) M.sdim[S.da]) * M.sstride[S.da] +
+                        (int64_t) (((uint32_t) M.sstart[S.db] + jb) % (uint32_t) M.sdim[S.db]) * M.sstride[S.db]];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t ja = (uint32_t) (a0 + ty + 8 * r), jb = (uint32_t) (b0 + tx);
+            if (ja < (uint32_t) M.size[S.da] && jb < (uint32_t) M.size[S.db]) {
+                dst[doff + (int64_t) (((uint32_t) M.dstart[S.da] + ja) % (uint32_t) M.ddim[S.da]) * M.dstride[S.da] +
+                        (int64_t) (((uint32_t) M.dstart[S.db] + jb) % (uint32_t) M.ddim[S.db]) * M.dstride[S.db]] =
+                        tile[tx][ty + 8 * r];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -153,11 +210,55 @@ int sstc_map_dev(int elem_bytes, const int32_t *bounds, int nbounds, const void 
         if (M.total == 0) {
             return;
         }
+        // fastest-varying dimension (smallest stride among extents > 1) on each side
+        int da = -1, db = -1;
+        for (int d = 0; d < nd; d++) {
+            if (M.size[d] > 1) {
+                if (da < 0 || M.sstride[d] < M.sstride[da]) {
+                    da = d;
+                }
+                if (db < 0 || M.dstride[d] < M.dstride[db]) {
+                    db = d;
+                }
+            }
+        }
+        if (da >= 0 && da != db && M.size[da] >= 16 && M.size[db] >= 16) {
+            MapTileSpec S;
+            S.da = da;
+            S.db = db;
+            S.ta = (M.size[da] + 31) / 32;
+            S.tb = (M.size[db] + 31) / 32;
+            S.rest = M.total / ((int64_t) M.size[da] * M.size[db]);
+            const int64_t ntiles = (int64_t) S.ta * S.tb * S.rest;
+            const int grid = (int) std::min<int64_t>(ntiles, (int64_t) sm_count() * 32);
+            if (elem_bytes == 8) {
+                map_tile_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst), M,
+                        S);
+            } else {
+                map_tile_kernel<int32_t><<<grid, 256, 0, s>>>(static_cast<const int32_t *>(src),
+                        static_cast<int32_t *>(dst), M, S);
+            }
+            check_launch("map_tile_kernel");
+            return;
+        }
         const int grid = stream_grid(M.total);
+        const bool small = M.total < (1LL << 31);
         if (elem_bytes == 8) {
-            map_kernel<double><<<grid, kThreads, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst), M);
+            const double *sp = static_cast<const double *>(src);
+            double *dp = static_cast<double *>(dst);
+            if (small) {
+                map_kernel<double, uint32_t><<<grid, kThreads, 0, s>>>(sp, dp, M);
+            } else {
+                map_kernel<double, uint64_t><<<grid, kThreads, 0, s>>>(sp, dp, M);
+            }
         } else {
-            map_kernel<int32_t><<<grid, kThreads, 0, s>>>(static_cast<const int32_t *>(src), static_cast<int32_t *>(dst), M);
+            const int32_t *sp = static_cast<const int32_t *>(src);
+            int32_t *dp = static_cast<int32_t *>(dst);
+            if (small) {
+                map_kernel<int32_t, uint32_t><<<grid, kThreads, 0, s>>>(sp, dp, M);
+            } else {
+                map_kernel<int32_t, uint64_t><<<grid, kThreads, 0, s>>>(sp, dp, M);
+            }
         }
         check_launch("map_kernel");
     });

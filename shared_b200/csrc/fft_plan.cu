@@ -14,6 +14,9 @@
 #include <mutex>
 #include <vector>
 
+#include <algorithm>
+
+#include "fft_aux_kernels.cuh"
 #include "fft_kernels.cuh"
 #include "sstc_internal.h"
 
@@ -219,6 +222,8 @@ static void launch_generic(const FftPassArgs &a, int L, cudaStream_t stream) {
 }
 
 static void dispatch_axis(const FftPassArgs &a, int L, bool strided, cudaStream_t stream);
+static void long_axis(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse,
+        double scale, cudaStream_t stream);
 
 // Optional blocked addressing of one side of a pass (see FftPassArgs).
 struct Blocks {
@@ -232,6 +237,15 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
         double scale, cudaStream_t stream, const Blocks &bin = Blocks(), const Blocks &bout = Blocks(),
         const int64_t *layout = nullptr, int reverse = 0) {
     if (outer <= 0 || inner <= 0 || L <= 0) {
+        return;
+    }
+    const bool is_pow2 = (L & (L - 1)) == 0;
+    if ((is_pow2 && L > 4096) || (!is_pow2 && L > kGenericMaxL)) {
+        // lengths the shared-memory kernels cannot hold: four-step (powers of two) or Bluestein (anything else)
+        if (bin.n > 0 || bout.n > 0 || layout) {
+            throw std::runtime_error("blocked / strided layouts need an axis length the tile kernels hold");
+        }
+        long_axis(in, out, outer, L, inner, mode, inverse, scale, stream);
         return;
     }
     FftPassArgs a;
@@ -302,6 +316,128 @@ static void dispatch_axis(const FftPassArgs &a, int L, bool strided, cudaStream_
     case 2048: launch_pow2_L<2048>(a, strided, stream); break;
     case 4096: launch_pow2_L<4096>(a, strided, stream); break;
     default: launch_generic(a, L, stream); break;
+    }
+}
+
+// ---- axes longer than the tile kernels hold ---------------------------------------------------------------
+// Powers of two above 4096: four-step, L = L1*L2 (both <= 4096): sub-pass over n1 -> twiddle w_L^{n2 k1} +
+// transpose -> sub-pass over n2; the result lands in natural order. Anything else above kGenericMaxL:
+// Bluestein (chirp-z) over power-of-two transforms of size M >= 2L-1. Both need a workspace of the size of the
+// data they touch, taken from per-thread grow-only scratch.
+
+static thread_local Scratch t_fft_ws[3];  // 0: Bluestein lines, 1: four-step transpose, 2: real<->complex staging
+static const int kMaxAxisLog2 = 24;
+static std::map<std::vector<int64_t>, double2 *> g_bluestein_filters;  // (device, L, M, inverse) -> FFT_M(b)
+
+static int grid_for(int64_t items) {
+    int64_t g = (items + 255) / 256;
+    return (int) std::max<int64_t>(1, std::min<int64_t>(g, 148 * 16));
+}
+
+static void fourstep_axis(const double2 *in, double2 *out, int64_t outer, int L, int64_t inner, int inverse,
+        double scale, cudaStream_t s) {
+    int lg = 0;
+    while ((1 << lg) < L) {
+        lg++;
+    }
+    if (lg > kMaxAxisLog2) {
+        throw std::runtime_error("FFT length " + std::to_string(L) + " exceeds the CUDA provider's 2^24 per-axis limit");
+    }
+    const int L1 = 1 << ((lg + 1) / 2), L2 = L / L1;
+    const int64_t n = outer * (int64_t) L * inner;
+    double2 *tmp = static_cast<double2 *>(t_fft_ws[1].get(n * 16));
+    launch_axis(in, tmp, outer, L1, (int64_t) L2 * inner, MODE_C2C, inverse, 1.0, s);
+    if (inner == 1) {
+        const int64_t tiles = outer * ((L1 + 31) / 32) * ((L2 + 31) / 32);
+        fourstep_twiddle_transpose_tile_kernel<<<(int) std::min<int64_t>(tiles, 148 * 32), 256, 0, s>>>(tmp, out, outer, L1, L2,
+                inverse);
+    } else {
+        fourstep_twiddle_transpose_kernel<<<grid_for(n), 256, 0, s>>>(tmp, out, outer, L1, L2, inner, inverse);
+    }
+    check_launch("fourstep_twiddle_transpose_kernel");
+    launch_axis(out, out, outer, L2, (int64_t) L1 * inner, MODE_C2C, inverse, scale, s);
+}
+
+static const double2 *bluestein_filter(int64_t L, int64_t M, int inverse, cudaStream_t s) {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    const std::vector<int64_t> key{dev, L, M, inverse};
+    {
+        std::lock_guard<std::mutex> lock(g_tw_mutex);
+        auto it = g_bluestein_filters.find(key);
+        if (it != g_bluestein_filters.end()) {
+            return it->second;
+        }
+    }
+    double2 *B = nullptr;
+    SSTC_CUDA(cudaMalloc(&B, (size_t) M * 16));
+    bluestein_filter_kernel<<<grid_for(M), 256, 0, s>>>(B, L, M, inverse);
+    check_launch("bluestein_filter_kernel");
+    launch_axis(B, B, 1, (int) M, 1, MODE_C2C, 0, 1.0, s);
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    g_bluestein_filters[key] = B;
+    return B;
+}
+
+static void bluestein_axis(const double2 *in, double2 *out, int64_t outer, int L, int64_t inner, int inverse,
+        double scale, cudaStream_t s) {
+    int64_t M = 1;
+    while (M < 2 * (int64_t) L - 1) {
+        M <<= 1;
+    }
+    if (M > (1LL << kMaxAxisLog2)) {
+        throw std::runtime_error("FFT length " + std::to_string(L) + " exceeds the CUDA provider's per-axis limit");
+    }
+    const double2 *Bf = bluestein_filter(L, M, inverse, s);
+    // whole planes (o) at a time, bounded to ~1 GiB of workspace
+    const int64_t per_plane = inner * M * 16;
+    const int64_t planes_per_chunk = std::max<int64_t>(1, (1LL << 30) / per_plane);
+    for (int64_t o0 = 0; o0 < outer; o0 += planes_per_chunk) {
+        const int64_t no = std::min(planes_per_chunk, outer - o0);
+        const int64_t lines = no * inner;
+        double2 *Y = static_cast<double2 *>(t_fft_ws[0].get(lines * M * 16));
+        const double2 *src = in + o0 * (int64_t) L * inner;
+        double2 *dst = out + o0 * (int64_t) L * inner;
+        bluestein_pre_kernel<<<grid_for(lines * M), 256, 0, s>>>(src, Y, no, L, inner, M, inverse);
+        check_launch("bluestein_pre_kernel");
+        launch_axis(Y, Y, lines, (int) M, 1, MODE_C2C, 0, 1.0, s);
+        bluestein_mul_kernel<<<grid_for(lines * M), 256, 0, s>>>(Y, Bf, lines, M);
+        check_launch("bluestein_mul_kernel");
+        launch_axis(Y, Y, lines, (int) M, 1, MODE_C2C, 1, 1.0 / (double) M, s);
+        bluestein_post_kernel<<<grid_for(no * (int64_t) L * inner), 256, 0, s>>>(Y, dst, no, L, inner, M, inverse, scale);
+        check_launch("bluestein_post_kernel");
+    }
+}
+
+static void long_axis(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse,
+        double scale, cudaStream_t s) {
+    const bool is_pow2 = (L & (L - 1)) == 0;
+    auto c2c = [&](const double2 *src, double2 *dst, double sc) {
+        if (is_pow2) {
+            fourstep_axis(src, dst, outer, L, inner, inverse, sc, s);
+        } else {
+            bluestein_axis(src, dst, outer, L, inner, inverse, sc, s);
+        }
+    };
+    if (mode == MODE_C2C) {
+        c2c(static_cast<const double2 *>(in), static_cast<double2 *>(out), scale);
+        return;
+    }
+    // real transforms on the last axis (inner == 1, outer = lines): stage through a full complex line
+    const int64_t n = outer * (int64_t) L;
+    double2 *full = static_cast<double2 *>(t_fft_ws[2].get(n * 16));
+    if (mode == MODE_R2C) {
+        real_to_complex_kernel<<<grid_for(n), 256, 0, s>>>(static_cast<const double *>(in), full, n);
+        check_launch("real_to_complex_kernel");
+        c2c(full, full, scale);
+        truncate_half_kernel<<<grid_for(n), 256, 0, s>>>(full, static_cast<double2 *>(out), outer, L);
+        check_launch("truncate_half_kernel");
+    } else {
+        hermitian_expand_kernel<<<grid_for(n), 256, 0, s>>>(static_cast<const double2 *>(in), full, outer, L);
+        check_launch("hermitian_expand_kernel");
+        c2c(full, full, scale);
+        complex_to_real_kernel<<<grid_for(n), 256, 0, s>>>(full, static_cast<double *>(out), n);
+        check_launch("complex_to_real_kernel");
     }
 }
 
@@ -467,9 +603,11 @@ static void build_plan(sstc_fft_plan_s &p) {
         const int L = s.axis_len;
         if (L >= 8 && L <= 4096 && (L & (L - 1)) == 0) {
             pow2_twiddles_for(L);
-        } else {
+        } else if (L <= kGenericMaxL && (L & (L - 1)) != 0) {
             twiddles_for(L);
-        }
+        } else if (L < 8) {
+            twiddles_for(L);
+        }  // longer axes build their tables (sub-pass twiddles, Bluestein filter) on first use
     }
 }
 

@@ -155,6 +155,7 @@ class SlabFft3d:
         self.engine = engine if engine is not None else CudaEngine(device if device is not None else 0)
         self.work = self.engine.empty(self.n_local)
         self._step = 0
+        self.replayed_kernels = 0  # kernels launched through CUDA-graph replays (not seen by sstc_launch_count)
         if exchange in ("p2p", "pipe"):
             dev = self.engine.device
             self.peer = [PeerBuffer(self.n_local, dev, group) for _ in range(2)]
@@ -225,8 +226,10 @@ class SlabFft3d:
         for parity in range(2):
             assert self._step % 2 == parity
             g = torch.cuda.CUDAGraph()
+            before = _lib.lib().sstc_launch_count()
             with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
                 out = self._forward_pipe(x)
+            self.graph_kernels = int(_lib.lib().sstc_launch_count() - before)  # kernels one replay launches
             self._graphs.append(g)
             self._graph_out.append(out)
         torch.cuda.synchronize(dev)
@@ -240,6 +243,7 @@ class SlabFft3d:
                 parity = self._step % 2
                 self._step += 1
                 self._graphs[parity].replay()
+                self.replayed_kernels += self.graph_kernels
                 return self._graph_out[parity]
             return self._forward_pipe(x)
         e, p = self.engine, self.world

@@ -102,6 +102,8 @@ DIMS = [
     [12, 4096], [2048, 6], [96, 80],
     [3, 3, 3], [4, 6, 5], [8, 8, 8], [64, 64, 64], [128, 32, 16], [5, 512, 3], [2, 4, 1, 8],
     [5, 6, 5, 6, 5], [2, 3, 4, 5, 6],
+    # axes longer than the tile kernels hold: four-step (powers of two) and Bluestein (anything else)
+    [8192], [65536], [1 << 20], [16384, 3], [3, 8192], [10007], [9000], [7, 12000], [12000, 5], [2, 7200, 3],
 ]
 
 
