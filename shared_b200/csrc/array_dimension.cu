@@ -18,6 +18,7 @@
 #include <limits.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "array_common.cuh"
@@ -308,45 +309,44 @@ __global__ void __launch_bounds__(kThreads) scan_lines_block_kernel(const double
         int64_t ioff, ooff;
         line_base(L, m, ioff, ooff);
         double carry = ident;
+        // A round covers 256 * kScanItems points; warp w owns the contiguous run of 32 * kScanItems points
+        // starting at base + w*32*kScanItems and walks it in kScanItems coalesced 32-point steps, scanning each
+        // step with shuffles and chaining the steps through lane 31 -- no shared memory inside a warp's run.
         for (int64_t base = 0; base < L.len; base += (int64_t) blockDim.x * kScanItems) {
-            const int64_t j0 = base + (int64_t) threadIdx.x * kScanItems;
+            const int64_t w0 = base + (int64_t) warp * 32 * kScanItems;
             double x[kScanItems];
+            double run = ident;  // inclusive total of this warp's run so far
 #pragma unroll
             for (int e = 0; e < kScanItems; e++) {
-                x[e] = j0 + e < L.len ? in[ioff + (j0 + e) * L.ilstride] : ident;
-            }
-#pragma unroll
-            for (int e = 1; e < kScanItems; e++) {
-                x[e] = rd_combine<OP>(x[e - 1], x[e]);
-            }
-            double tot = x[kScanItems - 1];  // inclusive scan of the thread totals across the warp
-            for (int off = 1; off < 32; off <<= 1) {
-                double y = __shfl_up_sync(0xffffffffu, tot, off);
-                if (lane >= off) {
-                    tot = rd_combine<OP>(y, tot);
+                const int64_t j = w0 + e * 32 + lane;
+                double v = j < L.len ? in[ioff + j * L.ilstride] : ident;
+                for (int off = 1; off < 32; off <<= 1) {
+                    double y = __shfl_up_sync(0xffffffffu, v, off);
+                    if (lane >= off) {
+                        v = rd_combine<OP>(y, v);
+                    }
                 }
+                v = rd_combine<OP>(run, v);
+                run = __shfl_sync(0xffffffffu, v, 31);
+                x[e] = v;
             }
-            if (lane == 31) {
-                warp_tot[warp] = tot;
-            }
-            double excl = __shfl_up_sync(0xffffffffu, tot, 1);  // exclusive prefix within the warp
             if (lane == 0) {
-                excl = ident;
+                warp_tot[warp] = run;
             }
             __syncthreads();
             double pre = carry;
             for (int w = 0; w < warp; w++) {
                 pre = rd_combine<OP>(pre, warp_tot[w]);
             }
-            pre = rd_combine<OP>(pre, excl);
 #pragma unroll
             for (int e = 0; e < kScanItems; e++) {
-                if (j0 + e < L.len) {
-                    out[ooff + (j0 + e) * L.olstride] = rd_combine<OP>(pre, x[e]);
+                const int64_t j = w0 + e * 32 + lane;
+                if (j < L.len) {
+                    out[ooff + j * L.olstride] = rd_combine<OP>(pre, x[e]);
                 }
             }
             if (threadIdx.x == blockDim.x - 1) {
-                carry_s = rd_combine<OP>(pre, x[kScanItems - 1]);
+                carry_s = rd_combine<OP>(pre, run);
             }
             __syncthreads();
             carry = carry_s;
@@ -454,74 +454,76 @@ __device__ __forceinline__ bool ri_pred(double x, double ext) {
     return OP == RI_ZERO ? x == 0.0 : OP == RI_GZERO ? x > 0.0 : OP == RI_LZERO ? x < 0.0 : x == ext;
 }
 
-// CTA per line: (1) extreme for MAX / MIN, (2) positions of the matching points in ascending order packed at
-// the front of the line, then -1 (DimensionOps.java:186-199).
-template <int OP>
+// CTA per line: (1) one coalesced read of the line (cached in shared memory when it fits) and, for MAX / MIN,
+// the extreme; (2) every warp counts the matches in its contiguous run of the line; (3) after one prefix over
+// the warp counts, every warp rewrites its matches' positions in ascending order behind the earlier warps',
+// then the tail is filled with -1 (DimensionOps.java:186-199). Three CTA barriers per line in total.
+template <int OP, bool CACHE>
 __global__ void __launch_bounds__(kThreads) index_lines_block_kernel(const double *__restrict__ in, int32_t *out,
         Lines L) {
+    extern __shared__ double sline[];
     __shared__ double part[kThreads / 32];
     __shared__ int warp_cnt[kThreads / 32];
-    __shared__ double ext_s;
-    __shared__ int base_s;
+    constexpr int NW = kThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chunk = ((L.len + NW - 1) / NW + 31) / 32 * 32;  // per-warp run, a multiple of 32
     for (int64_t m = blockIdx.x; m < L.n_lines; m += gridDim.x) {
         int64_t ioff, ooff;
         line_base(L, m, ioff, ooff);
         double ext = 0.0;
-        if (OP == RI_MAX || OP == RI_MIN) {
+        if (CACHE || OP == RI_MAX || OP == RI_MIN) {
             double acc = OP == RI_MAX ? -DBL_MAX : DBL_MAX;
             for (int64_t j = threadIdx.x; j < L.len; j += blockDim.x) {
-                double x = in[ioff + j * L.ilstride];
-                acc = OP == RI_MAX ? java_max(acc, x) : java_min(acc, x);
-            }
-            for (int off = 16; off > 0; off >>= 1) {
-                double o = __shfl_down_sync(0xffffffffu, acc, off);
-                acc = OP == RI_MAX ? java_max(acc, o) : java_min(acc, o);
-            }
-            if (lane == 0) {
-                part[warp] = acc;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int w = 1; w < kThreads / 32; w++) {
-                    acc = OP == RI_MAX ? java_max(acc, part[w]) : java_min(acc, part[w]);
+                const double x = in[ioff + j * L.ilstride];
+                if (CACHE) {
+                    sline[j] = x;
                 }
-                ext_s = acc;
+                if (OP == RI_MAX) {
+                    acc = java_max(acc, x);
+                } else if (OP == RI_MIN) {
+                    acc = java_min(acc, x);
+                }
+            }
+            if (OP == RI_MAX || OP == RI_MIN) {
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double o = __shfl_down_sync(0xffffffffu, acc, off);
+                    acc = OP == RI_MAX ? java_max(acc, o) : java_min(acc, o);
+                }
+                if (lane == 0) {
+                    part[warp] = acc;
+                }
             }
             __syncthreads();
-            ext = ext_s;
+            if (OP == RI_MAX || OP == RI_MIN) {
+                ext = part[0];
+                for (int w = 1; w < NW; w++) {
+                    ext = OP == RI_MAX ? java_max(ext, part[w]) : java_min(ext, part[w]);
+                }
+            }
         }
-        if (threadIdx.x == 0) {
-            base_s = 0;
+        const int64_t lo = warp * chunk, hi = lo + chunk < L.len ? lo + chunk : L.len;
+        int cnt = 0;
+        for (int64_t j = lo + lane; j < lo + chunk; j += 32) {
+            const bool hit = j < hi && ri_pred<OP>(CACHE ? sline[j] : in[ioff + j * L.ilstride], ext);
+            cnt += __popc(__ballot_sync(0xffffffffu, hit));
+        }
+        if (lane == 0) {
+            warp_cnt[warp] = cnt;
         }
         __syncthreads();
-        for (int64_t base = 0; base < L.len; base += blockDim.x) {
-            const int64_t j = base + threadIdx.x;
-            const bool hit = j < L.len && ri_pred<OP>(in[ioff + j * L.ilstride], ext);
-            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) {
-                warp_cnt[warp] = __popc(ballot);
-            }
-            __syncthreads();
-            int pre = base_s;
-            for (int w = 0; w < warp; w++) {
-                pre += warp_cnt[w];
-            }
-            if (hit) {
-                const int slot = pre + __popc(ballot & ((1u << lane) - 1u));
-                out[ooff + (int64_t) slot * L.olstride] = (int32_t) j;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int tot = base_s;
-                for (int w = 0; w < kThreads / 32; w++) {
-                    tot += warp_cnt[w];
-                }
-                base_s = tot;
-            }
-            __syncthreads();
+        int pos = 0, total = 0;
+        for (int w = 0; w < NW; w++) {
+            pos += w < warp ? warp_cnt[w] : 0;
+            total += warp_cnt[w];
         }
-        const int total = base_s;
+        for (int64_t j = lo + lane; j < lo + chunk; j += 32) {
+            const bool hit = j < hi && ri_pred<OP>(CACHE ? sline[j] : in[ioff + j * L.ilstride], ext);
+            const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                out[ooff + (int64_t) (pos + __popc(ballot & ((1u << lane) - 1u))) * L.olstride] = (int32_t) j;
+            }
+            pos += __popc(ballot);
+        }
         for (int64_t j = total + threadIdx.x; j < L.len; j += blockDim.x) {
             out[ooff + j * L.olstride] = -1;
         }
@@ -566,7 +568,19 @@ static void index_dim(const double *in, int32_t *out, const Lines &L, cudaStream
     }
     if (line_is_fastest(L) && L.len >= 64) {
         int grid = (int) std::min<int64_t>(L.n_lines, (int64_t) sm_count() * 16);
-        index_lines_block_kernel<OP><<<grid, kThreads, 0, s>>>(in, out, L);
+        constexpr int kCacheMax = 12288;  // 96 KB of shared memory: two lines resident per SM
+        if (L.len <= kCacheMax && (OP == RI_MAX || OP == RI_MIN)) {
+            static std::once_flag once[16];
+            int dev = 0;
+            SSTC_CUDA(cudaGetDevice(&dev));
+            std::call_once(once[dev & 15], [] {
+                SSTC_CUDA(cudaFuncSetAttribute(index_lines_block_kernel<OP, true>,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize, kCacheMax * 8));
+            });
+            index_lines_block_kernel<OP, true><<<grid, kThreads, (size_t) L.len * 8, s>>>(in, out, L);
+        } else {
+            index_lines_block_kernel<OP, false><<<grid, kThreads, 0, s>>>(in, out, L);
+        }
     } else {
         index_lines_thread_kernel<OP><<<(unsigned) ((L.n_lines + kThreads - 1) / kThreads), kThreads, 0, s>>>(in, out, L);
     }

@@ -44,6 +44,40 @@ __global__ void __launch_bounds__(kThreads) map_kernel(const T *__restrict__ src
     }
 }
 
+// Long last dimension (the common subarray / shift / tile / pad case): a CTA walks whole rows of the map, the
+// leading-dimension offsets are computed once per row and each thread only tracks its wrapped index along the
+// last dimension incrementally -- no division in the inner loop.
+template <class T>
+__global__ void __launch_bounds__(kThreads) map_rows_kernel(const T *__restrict__ src, T *dst, MapSpec M, int64_t rows,
+        int chunks) {
+    const int last = M.nd - 1;
+    const uint32_t n = (uint32_t) M.size[last], sdim = (uint32_t) M.sdim[last], ddim = (uint32_t) M.ddim[last];
+    const int64_t ss = M.sstride[last], ds = M.dstride[last];
+    const uint32_t per = (n + chunks - 1) / chunks;  // a long row is cut into `chunks` pieces, one CTA each
+    for (int64_t w = blockIdx.x; w < rows * chunks; w += gridDim.x) {
+        int64_t rem = w / chunks;
+        const uint32_t j0 = (uint32_t) (w % chunks) * per, j1 = j0 + per < n ? j0 + per : n;
+        int64_t soff = 0, doff = 0;
+        for (int d = last - 1; d >= 0; d--) {
+            const int64_t q = rem / M.size[d];
+            const uint32_t j = (uint32_t) (rem - q * M.size[d]);
+            rem = q;
+            soff += (int64_t) (((uint32_t) M.sstart[d] + j) % (uint32_t) M.sdim[d]) * M.sstride[d];
+            doff += (int64_t) (((uint32_t) M.dstart[d] + j) % (uint32_t) M.ddim[d]) * M.dstride[d];
+        }
+        uint32_t j = j0 + threadIdx.x;
+        uint32_t si = ((uint32_t) M.sstart[last] + j) % sdim, di = ((uint32_t) M.dstart[last] + j) % ddim;
+        const uint32_t sstep = kThreads % sdim, dstep = kThreads % ddim;
+        for (; j < j1; j += kThreads) {
+            dst[doff + (int64_t) di * ds] = src[soff + (int64_t) si * ss];
+            si += sstep;
+            si = si >= sdim ? si - sdim : si;
+            di += dstep;
+            di = di >= ddim ? di - ddim : di;
+        }
+    }
+}
+
 // When the fastest-varying dimension differs between source and destination (transposes, reverseOrder), a
 // thread-per-element copy is uncoalesced on one side. This kernel moves 32 x 32 tiles over (A = the source's
 // fastest dimension, B = the destination's) through shared memory: loads run along A, stores along B.
@@ -239,6 +273,22 @@ int sstc_map_dev(int elem_bytes, const int32_t *bounds, int nbounds, const void 
                         static_cast<int32_t *>(dst), M, S);
             }
             check_launch("map_tile_kernel");
+            return;
+        }
+        if (nd >= 1 && M.size[nd - 1] >= 512) {
+            const int64_t rows = M.total / M.size[nd - 1];
+            // enough CTAs to fill the machine: cut long rows when there are few of them
+            const int64_t want = (int64_t) sm_count() * 8;
+            int chunks = (int) std::max<int64_t>(1, std::min<int64_t>((want + rows - 1) / rows, M.size[nd - 1] / 512));
+            const int grid = (int) std::min<int64_t>(rows * chunks, want * 4);
+            if (elem_bytes == 8) {
+                map_rows_kernel<double><<<grid, kThreads, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst),
+                        M, rows, chunks);
+            } else {
+                map_rows_kernel<int32_t><<<grid, kThreads, 0, s>>>(static_cast<const int32_t *>(src),
+                        static_cast<int32_t *>(dst), M, rows, chunks);
+            }
+            check_launch("map_rows_kernel");
             return;
         }
         const int grid = stream_grid(M.total);

@@ -306,6 +306,19 @@ def test_map_slice_match_reference(k):
                 k.slice(slices, src, sdims, strides(sdims, order), a, ddims, strides(ddims, order))
                 ref.slice(slices, src, sdims, strides(sdims, order), b, ddims, strides(ddims, order))
                 assert np.array_equal(a, b), (sdims, ddims, slices)
+    # long last dimension (row-walking kernel) and mixed storage orders (tile-transposing kernel), with wrap / tiling
+    for sdims, ddims, so, do in [([3, 700], [5, 1100], "FAR", "FAR"), ([2, 3, 1500], [3, 2, 900], "FAR", "FAR"),
+                                 ([33, 47], [50, 41], "FAR", "NEAR"), ([40, 70, 3], [64, 64, 5], "NEAR", "FAR")]:
+        ns, ndd = int(np.prod(sdims)), int(np.prod(ddims))
+        src = rng.uniform(-1, 1, ns)
+        for trial in range(6):
+            bounds = []
+            for d in range(len(sdims)):
+                bounds += [int(rng.integers(-9, 9)), int(rng.integers(-9, 9)), int(rng.integers(0, 2 * ddims[d] + 1))]
+            a, b = np.full(ndd, 77.0), np.full(ndd, 77.0)
+            k.map(bounds, src, sdims, strides(sdims, so), a, ddims, strides(ddims, do))
+            ref.map(bounds, src, sdims, strides(sdims, so), b, ddims, strides(ddims, do))
+            assert np.array_equal(a, b), (sdims, ddims, bounds)
     # transpose expressed as permuted destination strides (ProtoArray.java:303-309)
     src = np.arange(24, dtype=np.float64)
     a, b = np.zeros(24), np.zeros(24)
