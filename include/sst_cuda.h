@@ -217,6 +217,28 @@ int sstc_mul_dev(const double *lhs, int64_t nl, const double *rhs, int64_t nr, i
 int sstc_diag(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex);
 int sstc_diag_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex, void *stream);
 
+/* ---- ImageKernel ------------------------------------------------------------------------------------
+ *
+ * The reference library's second native service (org.shared.image.kernel.ImageKernel,
+ * src/org/shared/image/kernel/ImageKernel.java:56-80; native methods org.shared.image.jni.NativeImageKernel,
+ * JNI exports native/src/shared/Bindings.cpp:144-158, bodies native/src/shared/NativeImageKernel.cpp:32-247;
+ * registered by JNI_OnLoad next to the ArrayKernel, native/src/shared_common/Library.cpp:64-66).
+ * dst has every source dimension + 1 (histogram: plus a trailing bins dimension of dD[nd] entries); the source
+ * lands at offset +1 along every dimension (histogram: in the bin mem[] names), the rest of dst is left as
+ * passed, and an inclusive running sum is taken along dimensions 0..nd-1 in turn. Errors: "Invalid arguments",
+ * "Invalid dimensions and/or strides", "Dimension mismatch", "Invalid membership index". */
+int sstc_integral_image(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, double *dst,
+        int64_t ndst, const int32_t *dD, const int32_t *dS, int nd);
+int sstc_integral_image_dev(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, double *dst,
+        int64_t ndst, const int32_t *dD, const int32_t *dS, int nd, void *stream);
+/* sD / sS have nd entries, dD / dS nd + 1; mem[] (int32 class memberships) is addressed like src. The device
+ * twin synchronises `stream` once (the membership check must finish before dst is touched). */
+int sstc_integral_histogram(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd,
+        const int32_t *mem, int64_t nmem, double *dst, int64_t ndst, const int32_t *dD, const int32_t *dS);
+int sstc_integral_histogram_dev(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd,
+        const int32_t *mem, int64_t nmem, double *dst, int64_t ndst, const int32_t *dD, const int32_t *dS,
+        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@
  *
  * oracle/Makefile compiles this file together with the UNMODIFIED sources
  * /root/reference/native/src/shared/{Common,ElementOps,DimensionOps*,MappingOps*,MatrixOps,NativeArrayKernel,
- * IndexOps}.cpp (read where they lie; never copied) against the shim oracle/ref/jni.h into
+ * IndexOps,NativeImageKernel}.cpp (read where they lie; never copied) against the shim oracle/ref/jni.h into
  * oracle/_ref/libsst_ref.so. The parity tests call these wrappers; each one builds the {kind,data,len} array
  * records the shim uses for Java arrays and forwards to the function the JNI export table binds
  * (native/src/shared/Bindings.cpp:26-142). A Java exception shows up as return code 1 + sstref_last_error().
@@ -166,6 +166,25 @@ int sstref_diag(const double *src, int nsrc, double *dst, int ndst, int size, in
     JNIEnv *env = env_get();
     _jobject s = DARR(src, nsrc), d = DARR(dst, ndst);
     MatrixOps::diag(env, 0, &s, &d, size, complex ? JNI_TRUE : JNI_FALSE);
+    return env_done(env);
+}
+
+/* NativeImageKernel (Bindings.cpp:144-158) */
+int sstref_integral_image(const double *src, int nsrc, const int *sD, const int *sS, double *dst, int ndst,
+        const int *dD, const int *dS, int nd) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), d = DARR(dst, ndst), dd = IARR(dD, nd),
+             ds = IARR(dS, nd);
+    NativeImageKernel::createIntegralImage(env, 0, &s, &sd, &ss, &d, &dd, &ds);
+    return env_done(env);
+}
+
+int sstref_integral_histogram(const double *src, int nsrc, const int *sD, const int *sS, int nd, const int *mem,
+        int nmem, double *dst, int ndst, const int *dD, const int *dS) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), m = IARR(mem, nmem), d = DARR(dst, ndst),
+             dd = IARR(dD, nd + 1), ds = IARR(dS, nd + 1);
+    NativeImageKernel::createIntegralHistogram(env, 0, &s, &sd, &ss, &m, &d, &dd, &ds);
     return env_done(env);
 }
 

@@ -128,6 +128,22 @@ class RefKernel:
         self._chk(self._l.sstref_diag(_p(_f64(srcV)), srcV.size, _p(_f64(dstV)), dstV.size, int(size),
                                       int(bool(complex_))))
 
+    # -- ImageKernel (src/org/shared/image/kernel/ImageKernel.java:56-80) -------------------------------------
+    def createIntegralImage(self, srcV, srcD, srcS, dstV, dstD, dstS):
+        sD, sS, dD, dS = _i32(srcD), _i32(srcS), _i32(dstD), _i32(dstS)
+        if not (sD.size == sS.size == dD.size == dS.size):
+            raise RefKernelError("Invalid arguments")
+        self._chk(self._l.sstref_integral_image(_p(_f64(srcV)), srcV.size, _p(sD), _p(sS), _p(_f64(dstV)), dstV.size,
+                                                _p(dD), _p(dS), sD.size))
+
+    def createIntegralHistogram(self, srcV, srcD, srcS, memV, dstV, dstD, dstS):
+        sD, sS, dD, dS = _i32(srcD), _i32(srcS), _i32(dstD), _i32(dstS)
+        assert memV.dtype == np.int32
+        if not (sD.size == sS.size and dD.size == dS.size == sD.size + 1):
+            raise RefKernelError("Invalid arguments")
+        self._chk(self._l.sstref_integral_histogram(_p(_f64(srcV)), srcV.size, _p(sD), _p(sS), sD.size, _p(memV),
+                                                    memV.size, _p(_f64(dstV)), dstV.size, _p(dD), _p(dS)))
+
 
 def load():
     """RefKernel, or None if oracle/_ref/libsst_ref.so is absent (it is built only where /root/reference exists

@@ -239,4 +239,35 @@ int sstc_diag(const double *src, int64_t nsrc, double *dst, int64_t ndst, int si
     });
 }
 
+// ---- ImageKernel (org.shared.image.jni.NativeImageKernel, Bindings.cpp:144-158) -----------------------------
+
+int sstc_integral_image(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, double *dst,
+        int64_t ndst, const int32_t *dD, const int32_t *dS, int nd) {
+    return guarded([&] {
+        if (nsrc < 0 || ndst < 0 || (nsrc > 0 && !src) || (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        // dst is uploaded too: its border takes part in the sums as it is (NativeImageKernel.cpp:96-118)
+        Staged s0(0, src, nsrc * 8, true), d(1, dst, ndst * 8, true);
+        rethrow(sstc_integral_image_dev(static_cast<const double *>(s0.dev), nsrc, sD, sS, static_cast<double *>(d.dev),
+                ndst, dD, dS, nd, nullptr));
+        d.download();
+        finish();
+    });
+}
+
+int sstc_integral_histogram(const double *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd,
+        const int32_t *mem, int64_t nmem, double *dst, int64_t ndst, const int32_t *dD, const int32_t *dS) {
+    return guarded([&] {
+        if (nsrc < 0 || nmem < 0 || ndst < 0 || (nsrc > 0 && !src) || (nmem > 0 && !mem) || (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        Staged s0(0, src, nsrc * 8, true), m(2, mem, nmem * 4, true), d(1, dst, ndst * 8, true);
+        rethrow(sstc_integral_histogram_dev(static_cast<const double *>(s0.dev), nsrc, sD, sS, nd,
+                static_cast<const int32_t *>(m.dev), nmem, static_cast<double *>(d.dev), ndst, dD, dS, nullptr));
+        d.download();
+        finish();
+    });
+}
+
 }  // extern "C"

@@ -1,9 +1,10 @@
 // jni_glue.cpp -- the JNI face of libsst_cuda.so: one export per native method of the Java providers
-// org.sharedx.cuda.CudaArrayKernel / CudaFftService (shared_b200/java), each a pin -> host-tier C ABI call ->
+// org.sharedx.cuda.CudaArrayKernel / CudaImageKernel / CudaFftService (shared_b200/java), each a pin -> host-tier C ABI call ->
 // release -> throw, plus the JNI_OnLoad that registers both providers.
 //
 // It mirrors, symbol for symbol, what the reference's libsst / libsstx export for their providers:
 //   native/src/shared/Bindings.cpp:26-142        Java_org_shared_array_jni_NativeArrayKernel_*
+//   native/src/shared/Bindings.cpp:144-158       Java_org_shared_image_jni_NativeImageKernel_*
 //   native/src/sharedx/BindingsX.cpp:26-29       Java_org_sharedx_fftw_Plan_transform
 //   native/src/shared_common/Library.cpp:33-126  JNI_OnLoad / JNI_OnUnload, Services.registerService
 // Ownership follows native/include/shared/Common.hpp:134-145: every array is pinned with
@@ -240,7 +241,8 @@ JNIEXPORT jint JNICALL JNI_OnLoad(JavaVM *jvm, void *) {
     jfieldID init = env->GetStaticFieldID(g_library, "initialized", "Z");
     if (reg && init &&
             register_service(env, reg, "org/shared/array/kernel/ArrayKernel", "org/sharedx/cuda/CudaArrayKernel") &&
-            register_service(env, reg, "org/shared/fft/FftService", "org/sharedx/cuda/CudaFftService")) {
+            register_service(env, reg, "org/shared/fft/FftService", "org/sharedx/cuda/CudaFftService") &&
+            register_service(env, reg, "org/shared/image/kernel/ImageKernel", "org/sharedx/cuda/CudaImageKernel")) {
         env->SetStaticBooleanField(g_library, init, JNI_TRUE);
     }
     return JNI_VERSION_1_4;
@@ -505,6 +507,47 @@ JNIEXPORT void JNICALL AK(diag)(JNIEnv *env, jobject, jdoubleArray srcV, jdouble
     {
         Pin s(env, srcV, true), d(env, dstV, false);
         rc = sstc_diag(s.as<double>(), ns, d.as<double>(), nd, size, complex ? 1 : 0);
+    }
+    raise_last(env, rc);
+}
+
+// ---- ImageKernel (Bindings.cpp:144-158 -> NativeImageKernel.cpp:32-247) --------------------------------------------
+
+JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaImageKernel_createIntegralImage(JNIEnv *env, jobject,
+        jdoubleArray srcV, jintArray srcD, jintArray srcS, jdoubleArray dstV, jintArray dstD, jintArray dstS) {
+    if (!srcV || !srcD || !srcS || !dstV || !dstD || !dstS) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize ns = len(env, srcV), nd = len(env, dstV), rank = len(env, srcD);
+    if (rank != len(env, srcS) || rank != len(env, dstD) || rank != len(env, dstS)) {
+        return raise(env, "Invalid arguments");
+    }
+    int rc;
+    {
+        Pin s(env, srcV, true), sd(env, srcD, true), ss(env, srcS, true), d(env, dstV, false), dd(env, dstD, true),
+                ds(env, dstS, true);
+        rc = sstc_integral_image(s.as<double>(), ns, sd.as<int32_t>(), ss.as<int32_t>(), d.as<double>(), nd,
+                dd.as<int32_t>(), ds.as<int32_t>(), rank);
+    }
+    raise_last(env, rc);
+}
+
+JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaImageKernel_createIntegralHistogram(JNIEnv *env, jobject,
+        jdoubleArray srcV, jintArray srcD, jintArray srcS, jintArray memV, jdoubleArray dstV, jintArray dstD,
+        jintArray dstS) {
+    if (!srcV || !srcD || !srcS || !memV || !dstV || !dstD || !dstS) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize ns = len(env, srcV), nm = len(env, memV), nd = len(env, dstV), rank = len(env, srcD);
+    if (rank != len(env, srcS) || rank + 1 != len(env, dstD) || rank + 1 != len(env, dstS) || ns != nm) {
+        return raise(env, "Invalid arguments");
+    }
+    int rc;
+    {
+        Pin s(env, srcV, true), sd(env, srcD, true), ss(env, srcS, true), m(env, memV, true), d(env, dstV, false),
+                dd(env, dstD, true), ds(env, dstS, true);
+        rc = sstc_integral_histogram(s.as<double>(), ns, sd.as<int32_t>(), ss.as<int32_t>(), rank, m.as<int32_t>(), nm,
+                d.as<double>(), nd, dd.as<int32_t>(), ds.as<int32_t>());
     }
     raise_last(env, rc);
 }

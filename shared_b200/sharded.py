@@ -138,7 +138,7 @@ class SlabFft3d:
     """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
 
     def __init__(self, dims, group=None, exchange="pipe", engine=None, device=None, groups=None,
-                 exchange_ctas=None):
+                 exchange_ctas=None, chunks=None):
         if len(dims) != 3:
             raise ValueError("SlabFft3d needs three dimensions")
         self.group = group
@@ -170,6 +170,8 @@ class SlabFft3d:
             torch.cuda.synchronize(dev)
             dist.barrier(group)
             self._epoch = 0
+            self.chunks = next(c for c in (chunks or 1, 1) if self.x_loc % c == 0)
+            self.s_z = torch.cuda.Stream(dev)
             self.s_bar = torch.cuda.Stream(dev, priority=-1)
             self.s_x = torch.cuda.Stream(dev, priority=-1)  # its CTAs must win SM slots from the pending exchange CTAs
         elif exchange == "collective":
@@ -189,25 +191,43 @@ class SlabFft3d:
         e, p = self.engine, self.world
         dev = e.device
         cur = torch.cuda.current_stream(dev)
-        e.axis(x, self.work, self.x_loc, self.d1, self.d2)                                       # y, local
         buf = self.peer[self._step % 2]
         self._step += 1
-        dst = [buf.ptrs[q] + self.rank * self.block * 16 for q in range(p)]
+        base = [buf.ptrs[q] + self.rank * self.block * 16 for q in range(p)]
         yg = self.y_loc // self.groups
         cols = yg * self.d2                      # columns of the received (d0, y_loc*d2) array per group
         kstride = self.y_loc * self.d2
-        for g in range(self.groups):
-            e.lines_scatter(self.work, dst, self.x_loc, self.d1, self.d2, g * yg, yg,
-                            max_ctas=self.exchange_ctas)                                          # z + transpose
-            sent = cur.record_event()
-            self.s_bar.wait_event(sent)
-            with torch.cuda.stream(self.s_bar):
-                e.peer_barrier(self.flags.ptrs, self.rank, 0)  # self-counting epochs: graph-capturable
-                arrived = self.s_bar.record_event()
-            self.s_x.wait_event(arrived)
-            with torch.cuda.stream(self.s_x):
-                ptr = buf.local_ptr + g * cols * 16
-                e.axis_strided(ptr, ptr, 1, self.d0, cols, 0, kstride, 0, kstride)               # x on this group
+        # y pass, local, in C chunks of planes: the exchange of chunk c starts as soon as its planes are done and
+        # runs beside the y pass of chunk c+1 (C == 1: the whole y pass first)
+        C, xc = self.chunks, self.x_loc // self.chunks
+        plane = self.d1 * self.d2
+        x_ptr, w_ptr = x.data_ptr(), self.work.data_ptr()
+        y_done = []
+        for c in range(C):
+            off = c * xc * plane * 16
+            e.axis(x_ptr + off, w_ptr + off, xc, self.d1, self.d2)                                # y, local
+            y_done.append(cur.record_event())
+        with torch.cuda.stream(self.s_z):
+            for c in range(C):
+                self.s_z.wait_event(y_done[c])
+                src = w_ptr + c * xc * plane * 16
+                dst = [b + c * xc * kstride * 16 for b in base]
+                if c < C - 1:
+                    e.lines_scatter(src, dst, xc, self.d1, self.d2, 0, self.y_loc,
+                                    max_ctas=self.exchange_ctas)                                  # z + transpose
+                    continue
+                # last chunk: in G groups of y indices; group g is complete everywhere once its barrier passes
+                for g in range(self.groups):
+                    e.lines_scatter(src, dst, xc, self.d1, self.d2, g * yg, yg, max_ctas=self.exchange_ctas)
+                    sent = self.s_z.record_event()
+                    self.s_bar.wait_event(sent)
+                    with torch.cuda.stream(self.s_bar):
+                        e.peer_barrier(self.flags.ptrs, self.rank, 0)  # self-counting epochs: graph-capturable
+                        arrived = self.s_bar.record_event()
+                    self.s_x.wait_event(arrived)
+                    with torch.cuda.stream(self.s_x):
+                        ptr = buf.local_ptr + g * cols * 16
+                        e.axis_strided(ptr, ptr, 1, self.d0, cols, 0, kstride, 0, kstride)       # x on this group
         cur.wait_stream(self.s_x)
         return buf.tensor
 
@@ -217,8 +237,8 @@ class SlabFft3d:
         if self.exchange != "pipe":
             raise ValueError("capture() is for the 'pipe' exchange")
         dev = self.engine.device
-        for _ in range(2):  # warm up both parities eagerly (first-use attribute calls are not capturable)
-            self._forward_pipe(x)
+        for _ in range(2 + self._step % 2):  # warm up both parities eagerly (first-use attribute calls are not
+            self._forward_pipe(x)            # capturable) and leave the buffer parity at 0
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)
         self._graphs, self._graph_out, self._graph_in = [], [], x.data_ptr()

@@ -61,6 +61,11 @@ cases += [
     ("map transpose", 16 * N, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], [1, n])),
     ("map copy", 16 * N, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], far)),
 ]
+from shared_b200.image_kernel import DeviceImageKernel
+ik = DeviceImageKernel(0, torch.cuda.current_stream().cuda_stream)
+ii = torch.zeros((n + 1) * (n + 1), dtype=torch.float64, device="cuda")
+cases.append(("ImageKernel createIntegralImage (16 B/elt minimum)", 8 * N + 8 * (n + 1) * (n + 1),
+              lambda: ik.createIntegralImage(P, N, [n, n], far, ii.data_ptr(), ii.numel(), [n + 1, n + 1], [n + 1, 1])))
 z.copy_(x)
 res = {"shape": [n, n], "peak_gbs": peak, "ops": []}
 for name, nbytes, fn in cases:
