@@ -84,6 +84,17 @@ int sstc_fft_plan_launches(sstc_fft_plan plan);
  * fail with "Unknown hint" (JavaFftService.java:96-104). Not thread-safe against a concurrent execute. */
 int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value);
 
+/* Fused FFT-domain correlation on device-resident data -- ConvolutionCache.convolve(ComplexArray cIm, RealArray ker)
+ * (src/org/shared/fft/ConvolutionCache.java:99-114): d_out = rifft(d_spec .* d_kernel_spec)[0:out_dims[0], ...],
+ * a dense row-major real array of dims out_dims (out_dims[d] = dims[d] - kernelSize[d] + 1 <= dims[d]). `plan`
+ * is a C2R plan for the image dims; d_spec is the image's half-spectrum (what rfft returned), d_kernel_spec the
+ * cached conj(rfft(padded kernel)) (ConvolutionCache.createCacheable, :117-138; FftCache.java:83-105 keeps it).
+ * The reference runs eMul, rifft and subarray as three whole-array operations through JVM arrays; here the
+ * product is formed while the first inverse pass loads and the crop happens while the last pass stores, so the
+ * product, the full-size inverse and the index tables of subarray never exist. Neither input is modified. */
+int sstc_fft_convolve_dev(sstc_fft_plan plan, const double *d_spec, const double *d_kernel_spec, double *d_out,
+        const int32_t *out_dims, void *stream);
+
 /* One axis pass of a row-major complex array viewed as (outer, len, inner): the building block the
  * slab-sharded multi-GPU transform (shared_b200/sharded.py) composes around its exchange step.
  * `inverse` selects e^{+2 pi i jk/n}; every output is multiplied by `scale`. In place when d_in == d_out. */

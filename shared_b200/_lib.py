@@ -42,6 +42,8 @@ SIGNATURES = {
     "sstc_fft_plan_workspace": (ctypes.c_int64, [ctypes.c_void_p]),
     "sstc_fft_plan_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "sstc_fft_plan_set_hint": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "sstc_fft_convolve_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             c_i32_p, ctypes.c_void_p]),
     "sstc_fft_axis_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                          ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]),
     "sstc_fft_axis_strided_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,

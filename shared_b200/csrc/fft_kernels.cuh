@@ -59,6 +59,15 @@ struct FftPassArgs {
     // at blk[q] + (xl*ls_block_lines + yl)*L -- whole 16*L-byte lines per destination, which is what lets
     // the exchange pass of the slab transform run in groups that the next pass can start consuming.
     int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines;
+    // Fused convolution (EXT kernels and the any-length kernel; all off when mul == nullptr and crop_cols == 0):
+    //   mul        every point loaded by a c2c (natural layout) or c2r pass is first multiplied by mul[same index]
+    //              -- the eMul of ConvolutionCache.convolve folded into the first inverse pass;
+    //   crop_cols  a c2r pass stores only the first crop_cols reals of a line, at line pitch crop_cols, and its
+    //              lines are numbered in the CROPPED leading dims crop_out[] (row-major) and mapped back to the
+    //              full leading dims crop_in[] on load -- the subarray of convolve folded into the last pass.
+    const double2 *mul;
+    int crop_cols, crop_nd;
+    int32_t crop_in[4], crop_out[4];
     int64_t ntiles;      // tiles in this launch (set by the launcher); the grid may be smaller
     int64_t grid_limit;  // 0 = one CTA per tile
     int reverse;         // process the tiles in descending order
@@ -71,6 +80,18 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 w) {
 }
 // a * (-i)
 __device__ __forceinline__ double2 cmul_mi(double2 a) { return make_double2(a.y, -a.x); }
+
+// Line number in the cropped leading dims -> line number in the full leading dims (see FftPassArgs::crop_cols).
+__device__ __forceinline__ int64_t crop_source_line(const FftPassArgs &a, int64_t line) {
+    int64_t src = 0, mult = 1;
+    for (int d = a.crop_nd - 1; d >= 0; d--) {
+        const int64_t q = line / a.crop_out[d];
+        src += (line - q * a.crop_out[d]) * mult;
+        mult *= a.crop_in[d];
+        line = q;
+    }
+    return a.crop_nd > 0 ? src : line;
+}
 
 // In-register DFTs over v[0], v[S], v[2S], ... (forward sign), outputs in natural order at the same slots.
 template <int S>
@@ -279,6 +300,12 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
             for (int m = 0; m < 8; m++) {
                 v[m] = a.in[in_base + (int64_t) (t + m * T) * in_ks];
             }
+            if (EXT && a.mul) {
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    v[m] = cmul(v[m], a.mul[in_base + (int64_t) (t + m * T) * in_ks]);
+                }
+            }
         } else if (a.mode == MODE_R2C) {
             const double *rin = reinterpret_cast<const double *>(a.in) + line * L;
 #pragma unroll
@@ -286,16 +313,17 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
                 v[m] = make_double2(rin[t + m * T], 0.0);
             }
         } else {  // MODE_C2R: half-complex line of L/2+1 bins
-            const double2 *hin = a.in + line * (L / 2 + 1);
+            const int64_t hoff = (EXT && a.crop_cols > 0 ? crop_source_line(a, line) : line) * (L / 2 + 1);
+            const double2 *hin = a.in + hoff;
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                int p = t + m * T;
-                if (p <= L / 2) {
-                    v[m] = hin[p];
-                } else {
-                    double2 z = hin[L - p];
-                    v[m] = make_double2(z.x, -z.y);
+                const int p = t + m * T;
+                const int q = p <= L / 2 ? p : L - p;
+                double2 z = hin[q];
+                if (EXT && a.mul) {
+                    z = cmul(z, a.mul[hoff + q]);
                 }
+                v[m] = p <= L / 2 ? z : make_double2(z.x, -z.y);
             }
         }
         if (a.inverse) {
@@ -345,6 +373,14 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
             int p = t + m * T;
             if (p <= L / 2) {
                 hout[p] = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+            }
+        }
+    } else if (EXT && a.crop_cols > 0) {
+        double *rout = reinterpret_cast<double *>(a.out) + line * a.crop_cols;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            if (t + m * T < a.crop_cols) {
+                rout[t + m * T] = (a.inverse ? v[m].y : v[m].x) * s;
             }
         }
     } else {
@@ -405,6 +441,7 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g
     const int64_t i = blockIdx.x - o * a.inner;
     const int64_t line = blockIdx.x;  // r2c / c2r are launched with inner == 1
     const int half = L / 2 + 1;
+    const int64_t hoff = (a.crop_cols > 0 ? crop_source_line(a, line) : line) * half;  // c2r source line
 
     for (int p = threadIdx.x; p < L; p += blockDim.x) {
         double2 z;
@@ -413,14 +450,20 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g
             const int pk = p - q * a.in_ksplit;
             z = a.in_blk[q][(o * a.in_ksplit + pk) * a.in_blk_pitch + i];
         } else if (a.mode == MODE_C2C) {
-            z = a.in[o * a.in_plane + (int64_t) p * a.in_kstride + i];
+            const int64_t idx = o * a.in_plane + (int64_t) p * a.in_kstride + i;
+            z = a.in[idx];
+            if (a.mul) {
+                z = cmul(z, a.mul[idx]);
+            }
         } else if (a.mode == MODE_R2C) {
             z = make_double2(reinterpret_cast<const double *>(a.in)[line * L + p], 0.0);
         } else {
-            if (p < half) {
-                z = a.in[line * half + p];
-            } else {
-                z = a.in[line * half + (L - p)];
+            const int q = p < half ? p : L - p;
+            z = a.in[hoff + q];
+            if (a.mul) {
+                z = cmul(z, a.mul[hoff + q]);
+            }
+            if (p >= half) {
                 z.y = -z.y;
             }
         }
@@ -475,6 +518,10 @@ __global__ void __launch_bounds__(256) fft_generic_kernel(const FftGenericArgs g
         } else if (a.mode == MODE_R2C) {
             if (p < half) {
                 a.out[line * half + p] = z;
+            }
+        } else if (a.crop_cols > 0) {
+            if (p < a.crop_cols) {
+                reinterpret_cast<double *>(a.out)[line * a.crop_cols + p] = z.x;
             }
         } else {
             reinterpret_cast<double *>(a.out)[line * L + p] = z.x;

@@ -124,8 +124,8 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
         throw std::runtime_error("FFT batch too large for one launch");
     }
     // anything beyond "one tile per CTA, natural layout" runs the extended kernel
-    const bool ext = a.ksplit > 0 || a.in_ksplit > 0 || a.ls_group > 0 || a.grid_limit > 0 || a.reverse ||
-            (STRIDED && (a.in_kstride != a.inner || a.out_kstride != a.inner));
+    const bool ext = a.ksplit > 0 || a.in_ksplit > 0 || a.ls_group > 0 || a.grid_limit > 0 || a.reverse || a.mul ||
+            a.crop_cols > 0 || (STRIDED && (a.in_kstride != a.inner || a.out_kstride != a.inner));
     if (!ext) {
         fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
         check_launch("fft_pow2_kernel");
@@ -232,17 +232,28 @@ struct Blocks {
     int64_t pitch = 0;  // 0 = dense (== inner)
 };
 
+// Work folded into a pass by the fused convolution (see FftPassArgs::mul / crop_cols).
+struct Fuse {
+    const double2 *mul = nullptr;
+    int crop_cols = 0, crop_nd = 0;
+    int32_t crop_in[4] = {1, 1, 1, 1}, crop_out[4] = {1, 1, 1, 1};
+};
+
+static bool tile_kernels_hold(int L) {
+    const bool is_pow2 = (L & (L - 1)) == 0;
+    return is_pow2 ? L <= 4096 : L <= kGenericMaxL;
+}
+
 // One pass over axis `L` of (outer, L, inner). For MODE_R2C / MODE_C2R, inner must be 1 and outer counts lines.
 static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse,
         double scale, cudaStream_t stream, const Blocks &bin = Blocks(), const Blocks &bout = Blocks(),
-        const int64_t *layout = nullptr, int reverse = 0) {
+        const int64_t *layout = nullptr, int reverse = 0, const Fuse *fuse = nullptr) {
     if (outer <= 0 || inner <= 0 || L <= 0) {
         return;
     }
-    const bool is_pow2 = (L & (L - 1)) == 0;
-    if ((is_pow2 && L > 4096) || (!is_pow2 && L > kGenericMaxL)) {
+    if (!tile_kernels_hold(L)) {
         // lengths the shared-memory kernels cannot hold: four-step (powers of two) or Bluestein (anything else)
-        if (bin.n > 0 || bout.n > 0 || layout) {
+        if (bin.n > 0 || bout.n > 0 || layout || fuse) {
             throw std::runtime_error("blocked / strided layouts need an axis length the tile kernels hold");
         }
         long_axis(in, out, outer, L, inner, mode, inverse, scale, stream);
@@ -272,6 +283,13 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = 0;
     a.ntiles = a.grid_limit = 0;
     a.reverse = reverse;
+    a.mul = fuse ? fuse->mul : nullptr;
+    a.crop_cols = fuse ? fuse->crop_cols : 0;
+    a.crop_nd = fuse ? fuse->crop_nd : 0;
+    for (int d = 0; d < 4; d++) {
+        a.crop_in[d] = fuse ? fuse->crop_in[d] : 1;
+        a.crop_out[d] = fuse ? fuse->crop_out[d] : 1;
+    }
     a.blk_pitch = a.in_blk_pitch = inner;
     for (int q = 0; q < 8; q++) {
         a.blk[q] = nullptr;
@@ -628,6 +646,88 @@ static void execute_plan(sstc_fft_plan_s &p, const double *d_in, double *d_out, 
 
 static int plan_launches(const sstc_fft_plan_s &p) { return (int) p.steps.size(); }
 
+static thread_local Scratch t_conv_ws[2];  // unfused fallback of the convolution: product, full-size result
+
+// ConvolutionCache.convolve(ComplexArray cIm, RealArray ker) (ConvolutionCache.java:99-114) on a C2R plan:
+// out = rifft(spec .* kernel_spec)[0:out_dims[0], 0:out_dims[1], ...]. Fused whenever every axis fits the tile
+// kernels: the product is formed while the first pass loads, the crop happens while the last pass stores.
+static void execute_convolve(sstc_fft_plan_s &p, const double *d_spec, const double *d_kernel_spec, double *d_out,
+        const int32_t *out_dims, cudaStream_t stream) {
+    if (p.kind != SSTC_FFT_C2R) {
+        throw std::runtime_error("convolve needs a C2R plan");
+    }
+    if (!d_spec || !d_kernel_spec || !d_out || !out_dims) {
+        throw std::runtime_error("Invalid arguments");
+    }
+    const int rank = (int) p.dims.size();
+    int64_t out_lines = 1;
+    for (int d = 0; d < rank; d++) {
+        if (out_dims[d] <= 0 || out_dims[d] > p.dims[(size_t) d]) {
+            throw std::runtime_error("Invalid kernel size");  // ConvolutionCache.java:80-81
+        }
+        if (d < rank - 1) {
+            out_lines *= out_dims[d];
+        }
+    }
+    bool fusable = rank - 1 <= 4;
+    for (const Step &s : p.steps) {
+        fusable = fusable && tile_kernels_hold(s.axis_len);
+    }
+    if (!fusable) {
+        // product -> scratch, plain inverse -> scratch, strided copy of the valid block -> out
+        const int64_t nspec = p.in_len, nfull = p.out_len;
+        double *prod = static_cast<double *>(t_conv_ws[0].get(nspec * 8));
+        double *full = static_cast<double *>(t_conv_ws[1].get(nfull * 8));
+        if (sstc_eop_dev(2 /* CE_MUL */, SSTC_ELEM_COMPLEX, d_spec, d_kernel_spec, prod, nspec, stream) != 0) {
+            throw std::runtime_error(std::string(sstc_last_error()));
+        }
+        execute_plan(p, prod, full, stream);
+        std::vector<int32_t> bounds((size_t) 3 * rank), sD(p.dims), sS((size_t) rank), dD(out_dims, out_dims + rank),
+                dS((size_t) rank);
+        int64_t ss = 1, ds = 1, nout = 1;
+        for (int d = rank - 1; d >= 0; d--) {
+            sS[(size_t) d] = (int32_t) ss;
+            dS[(size_t) d] = (int32_t) ds;
+            ss *= p.dims[(size_t) d];
+            ds *= out_dims[d];
+            nout *= out_dims[d];
+            bounds[(size_t) 3 * d] = 0;
+            bounds[(size_t) 3 * d + 1] = 0;
+            bounds[(size_t) 3 * d + 2] = out_dims[d];
+        }
+        if (sstc_map_dev(8, bounds.data(), 3 * rank, full, nfull, sD.data(), sS.data(), d_out, nout, dD.data(), dS.data(),
+                    rank, stream) != 0) {
+            throw std::runtime_error(std::string(sstc_last_error()));
+        }
+        return;
+    }
+    const size_t ns = p.steps.size();
+    for (size_t k = 0; k < ns; k++) {
+        const Step &s = p.steps[k];
+        const void *src = s.src == 0 ? (const void *) d_spec : s.src == 1 ? (const void *) d_out : p.workspace;
+        void *dst = s.dst == 1 ? (void *) d_out : p.workspace;
+        Fuse f;
+        bool any = false;
+        int64_t outer = s.outer;
+        if (k == 0) {
+            f.mul = reinterpret_cast<const double2 *>(d_kernel_spec);
+            any = true;
+        }
+        if (k == ns - 1) {  // the c2r pass
+            f.crop_cols = out_dims[rank - 1];
+            f.crop_nd = rank - 1;
+            for (int d = 0; d < rank - 1; d++) {
+                f.crop_in[d] = p.dims[(size_t) d];
+                f.crop_out[d] = out_dims[d];
+            }
+            outer = out_lines;
+            any = true;
+        }
+        launch_axis(src, dst, outer, s.axis_len, s.inner, s.mode, p.inverse, s.scale, stream, Blocks(), Blocks(), nullptr, 0,
+                any ? &f : nullptr);
+    }
+}
+
 // Host-tier plan cache (FftwService keeps one too: FftwService.java:58-67,221-236). Guarded by one mutex;
 // host-tier calls are PCIe-bound, so serialising them costs nothing measurable.
 static std::mutex g_host_mutex;
@@ -719,6 +819,16 @@ int sstc_fft_plan_set_hint(sstc_fft_plan plan, const char *name, int64_t value) 
         } else {
             throw std::runtime_error("Unknown hint");
         }
+    });
+}
+
+int sstc_fft_convolve_dev(sstc_fft_plan plan, const double *d_spec, const double *d_kernel_spec, double *d_out,
+        const int32_t *out_dims, void *stream) {
+    return guarded([&] {
+        if (!plan) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        execute_convolve(*plan, d_spec, d_kernel_spec, d_out, out_dims, as_stream(stream));
     });
 }
 
