@@ -413,6 +413,59 @@ __global__ void __launch_bounds__(kThreads) scan_lines_thread_kernel(const doubl
     }
 }
 
+// Lines that are NOT along the fastest dimension, many of them (an image's columns): a CTA owns a strip of 32
+// adjacent lines (lane = line, so every row of the strip is one coalesced 256-byte access) and walks down it in
+// blocks of 8 warps x kStripRows rows: each warp scans its kStripRows rows in registers, the per-warp column
+// totals meet in shared memory, and a per-lane carry links the blocks. One pass: 8 B read + 8 B written per point.
+constexpr int kStripRows = 16;
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads) scan_strip_kernel(const double *in, double *out, Lines L) {
+    constexpr int NW = kThreads / 32;
+    __shared__ double tot[2][NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double ident = OP == RD_SUM ? 0.0 : 1.0;
+    const int64_t strips = (L.n_lines + 31) / 32;
+    for (int64_t sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
+        const int64_t m = sidx * 32 + lane;
+        const bool live = m < L.n_lines;
+        int64_t ioff = 0, ooff = 0;
+        if (live) {
+            line_base(L, m, ioff, ooff);
+        }
+        double carry = ident;
+        int buf = 0;
+        for (int64_t base = 0; base < L.len; base += (int64_t) NW * kStripRows, buf ^= 1) {
+            const int64_t r0 = base + (int64_t) warp * kStripRows;
+            double x[kStripRows];
+#pragma unroll
+            for (int e = 0; e < kStripRows; e++) {
+                x[e] = (live && r0 + e < L.len) ? in[ioff + (r0 + e) * L.ilstride] : ident;
+            }
+#pragma unroll
+            for (int e = 1; e < kStripRows; e++) {
+                x[e] = rd_combine<OP>(x[e - 1], x[e]);
+            }
+            tot[buf][warp][lane] = x[kStripRows - 1];
+            __syncthreads();  // tot[buf] is rewritten two blocks later, after the next barrier: no second barrier
+            double pre = carry;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const double t = tot[buf][w][lane];
+                pre = w < warp ? rd_combine<OP>(pre, t) : pre;
+                carry = rd_combine<OP>(carry, t);
+            }
+#pragma unroll
+            for (int e = 0; e < kStripRows; e++) {
+                if (live && r0 + e < L.len) {
+                    out[ooff + (r0 + e) * L.olstride] = rd_combine<OP>(pre, x[e]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 template <int OP>
 static void scan_dim(const double *in, double *out, const Lines &L, cudaStream_t s) {
     if (L.n_lines == 0 || L.len == 0) {
@@ -428,6 +481,12 @@ static void scan_dim(const double *in, double *out, const Lines &L, cudaStream_t
             scan_lines_warp_kernel<OP><<<grid, kThreads, 0, s>>>(in, out, L);
         }
         check_launch("scan_lines_kernel");
+        return;
+    }
+    if (L.n_lines >= (int64_t) sm_count() * 32 && L.len >= 64) {
+        const int grid = (int) std::min<int64_t>((L.n_lines + 31) / 32, (int64_t) sm_count() * 8);
+        scan_strip_kernel<OP><<<grid, kThreads, 0, s>>>(in, out, L);
+        check_launch("scan_strip_kernel");
         return;
     }
     const int64_t target = (int64_t) sm_count() * 2048;

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "array_common.cuh"
 
 namespace sstc {
@@ -87,10 +89,17 @@ struct MapTileSpec {
     int64_t rest;        // product of the other extents
 };
 
-template <class T>
+template <class T, int TS>
 __global__ void __launch_bounds__(256) map_tile_kernel(const T *__restrict__ src, T *dst, MapSpec M, MapTileSpec S) {
-    __shared__ T tile[32][33];
+    // TS x TS tiles, 256 threads as TS x (256 / TS): every thread moves TS * TS / 256 elements, all loads issued
+    // before the barrier. Wrapped indices advance by conditional subtraction, one modulo per thread and side.
+    constexpr int TY = 256 / TS, R = TS / TY;
+    __shared__ T tile[TS][TS + 1];
     const int64_t ntiles = (int64_t) S.ta * S.tb * S.rest;
+    const uint32_t na = (uint32_t) M.size[S.da], nb = (uint32_t) M.size[S.db];
+    const uint32_t sda = (uint32_t) M.sdim[S.da], sdb = (uint32_t) M.sdim[S.db];
+    const uint32_t dda = (uint32_t) M.ddim[S.da], ddb = (uint32_t) M.ddim[S.db];
+    const int tx = threadIdx.x % TS, ty = threadIdx.x / TS;
     for (int64_t blk = blockIdx.x; blk < ntiles; blk += gridDim.x) {
         int64_t rem = blk;
         const int ia = (int) (rem % S.ta);
@@ -108,25 +117,34 @@ __global__ void __launch_bounds__(256) map_tile_kernel(const T *__restrict__ src
             soff += (int64_t) (((uint32_t) M.sstart[d] + j) % (uint32_t) M.sdim[d]) * M.sstride[d];
             doff += (int64_t) (((uint32_t) M.dstart[d] + j) % (uint32_t) M.ddim[d]) * M.dstride[d];
         }
-        const int a0 = ia * 32, b0 = ib * 32;
-        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+        const uint32_t a0 = (uint32_t) ia * TS, b0 = (uint32_t) ib * TS;
+        {  // loads run along A (the source's fastest dimension)
+            const uint32_t ja = a0 + tx;
+            const int64_t pa = soff + (int64_t) (((uint32_t) M.sstart[S.da] + ja) % sda) * M.sstride[S.da];
+            uint32_t wb = ((uint32_t) M.sstart[S.db] + b0 + ty) % sdb;
+            const uint32_t step = TY % sdb;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t ja = (uint32_t) (a0 + tx), jb = (uint32_t) (b0 + ty + 8 * r);
-            if (ja < (uint32_t) M.size[S.da] && jb < (uint32_t) M.size[S.db]) {
-                tile[ty + 8 * r][tx] = src[soff +
-                        (int64_t) (((uint32_t) M.sstart[S.da] + ja) % (uint32_t) M.sdim[S.da]) * M.sstride[S.da] +
-                        (int64_t) (((uint32_t) M.sstart[S.db] + jb) % (uint32_t) M.sdim[S.db]) * M.sstride[S.db]];
+            for (int r = 0; r < R; r++) {
+                if (ja < na && b0 + ty + TY * r < nb) {
+                    tile[ty + TY * r][tx] = src[pa + (int64_t) wb * M.sstride[S.db]];
+                }
+                wb += step;
+                wb = wb >= sdb ? wb - sdb : wb;
             }
         }
         __syncthreads();
+        {  // stores run along B (the destination's fastest dimension)
+            const uint32_t jb = b0 + tx;
+            const int64_t pb = doff + (int64_t) (((uint32_t) M.dstart[S.db] + jb) % ddb) * M.dstride[S.db];
+            uint32_t wa = ((uint32_t) M.dstart[S.da] + a0 + ty) % dda;
+            const uint32_t step = TY % dda;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t ja = (uint32_t) (a0 + ty + 8 * r), jb = (uint32_t) (b0 + tx);
-            if (ja < (uint32_t) M.size[S.da] && jb < (uint32_t) M.size[S.db]) {
-                dst[doff + (int64_t) (((uint32_t) M.dstart[S.da] + ja) % (uint32_t) M.ddim[S.da]) * M.dstride[S.da] +
-                        (int64_t) (((uint32_t) M.dstart[S.db] + jb) % (uint32_t) M.ddim[S.db]) * M.dstride[S.db]] =
-                        tile[tx][ty + 8 * r];
+            for (int r = 0; r < R; r++) {
+                if (jb < nb && a0 + ty + TY * r < na) {
+                    dst[pb + (int64_t) wa * M.dstride[S.da]] = tile[tx][ty + TY * r];
+                }
+                wa += step;
+                wa = wa >= dda ? wa - dda : wa;
             }
         }
         __syncthreads();
@@ -260,16 +278,18 @@ int sstc_map_dev(int elem_bytes, const int32_t *bounds, int nbounds, const void 
             MapTileSpec S;
             S.da = da;
             S.db = db;
-            S.ta = (M.size[da] + 31) / 32;
-            S.tb = (M.size[db] + 31) / 32;
+            // 32 x 32 tiles; measured at 8192^2 doubles: 5360 GB/s, against 5050 GB/s for 64 x 64 tiles
+            constexpr int ts = 32;
+            S.ta = (M.size[da] + ts - 1) / ts;
+            S.tb = (M.size[db] + ts - 1) / ts;
             S.rest = M.total / ((int64_t) M.size[da] * M.size[db]);
             const int64_t ntiles = (int64_t) S.ta * S.tb * S.rest;
             const int grid = (int) std::min<int64_t>(ntiles, (int64_t) sm_count() * 32);
             if (elem_bytes == 8) {
-                map_tile_kernel<double><<<grid, 256, 0, s>>>(static_cast<const double *>(src), static_cast<double *>(dst), M,
-                        S);
+                map_tile_kernel<double, ts><<<grid, 256, 0, s>>>(static_cast<const double *>(src),
+                        static_cast<double *>(dst), M, S);
             } else {
-                map_tile_kernel<int32_t><<<grid, 256, 0, s>>>(static_cast<const int32_t *>(src),
+                map_tile_kernel<int32_t, ts><<<grid, 256, 0, s>>>(static_cast<const int32_t *>(src),
                         static_cast<int32_t *>(dst), M, S);
             }
             check_launch("map_tile_kernel");
