@@ -354,29 +354,43 @@ __global__ void __launch_bounds__(kThreads) scan_lines_block_kernel(const double
     }
 }
 
-// warp per line for short lines
+// Warp per line: short lines, or long ones when there are enough lines to fill the machine with warps (no CTA
+// barrier at all). kWarpSteps coalesced 32-point steps are loaded up front (2 KB in flight per warp), then scanned
+// one after another with shuffles, chained through lane 31.
+constexpr int kWarpSteps = 8;
+
 template <int OP>
 __global__ void __launch_bounds__(kThreads) scan_lines_warp_kernel(const double *in, double *out, Lines L) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    const double ident = OP == RD_SUM ? 0.0 : 1.0;
     for (int64_t m = (((int64_t) blockIdx.x * blockDim.x) + threadIdx.x) >> 5; m < L.n_lines; m += warps) {
         int64_t ioff, ooff;
         line_base(L, m, ioff, ooff);
-        double carry = OP == RD_SUM ? 0.0 : 1.0;
-        for (int64_t base = 0; base < L.len; base += 32) {
-            const int64_t j = base + lane;
-            double x = j < L.len ? in[ioff + j * L.ilstride] : (OP == RD_SUM ? 0.0 : 1.0);
-            for (int off = 1; off < 32; off <<= 1) {
-                double y = __shfl_up_sync(0xffffffffu, x, off);
-                if (lane >= off) {
-                    x = rd_combine<OP>(y, x);
+        double carry = ident;
+        for (int64_t base = 0; base < L.len; base += 32 * kWarpSteps) {
+            double x[kWarpSteps];
+#pragma unroll
+            for (int e = 0; e < kWarpSteps; e++) {
+                const int64_t j = base + e * 32 + lane;
+                x[e] = j < L.len ? in[ioff + j * L.ilstride] : ident;
+            }
+#pragma unroll
+            for (int e = 0; e < kWarpSteps; e++) {
+                const int64_t j = base + e * 32 + lane;
+                double v = x[e];
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, v, off);
+                    if (lane >= off) {
+                        v = rd_combine<OP>(y, v);
+                    }
                 }
+                v = rd_combine<OP>(carry, v);
+                if (j < L.len) {
+                    out[ooff + j * L.olstride] = v;
+                }
+                carry = __shfl_sync(0xffffffffu, v, 31);
             }
-            x = rd_combine<OP>(carry, x);
-            if (j < L.len) {
-                out[ooff + j * L.olstride] = x;
-            }
-            carry = __shfl_sync(0xffffffffu, x, 31);
         }
     }
 }
@@ -472,7 +486,7 @@ static void scan_dim(const double *in, double *out, const Lines &L, cudaStream_t
         return;
     }
     if (line_is_fastest(L)) {
-        if (L.len > 256) {
+        if (L.len > 256 && L.n_lines < (int64_t) sm_count() * 32) {
             int grid = (int) std::min<int64_t>(L.n_lines, (int64_t) sm_count() * 16);
             scan_lines_block_kernel<OP><<<grid, kThreads, 0, s>>>(in, out, L);
         } else {

@@ -122,7 +122,7 @@ SHAPES = [([7], "FAR"), ([3, 4, 5], "FAR"), ([3, 4, 5], "NEAR"), ([6, 1, 5], "FA
           ([2, 3, 4, 5, 6], "NEAR"), ([300, 70], "FAR"), ([70, 300], "NEAR"), ([5, 2100], "FAR"), ([2100, 5], "FAR"),
           ([17, 33, 9], "FAR"), ([1, 1, 1], "FAR"), ([4096], "FAR"),
           # many long lines off the fastest dimension: the strip scan / thread-per-line folds
-          ([130, 5000], "FAR"), ([5000, 200], "NEAR"), ([70, 40, 130], "FAR")]
+          ([130, 5000], "FAR"), ([5000, 200], "NEAR"), ([70, 40, 130], "FAR"), ([5000, 300], "FAR")]
 
 
 @needs_ref
