@@ -33,6 +33,7 @@ struct FftPassArgs {
     double2 *out;        // c2c / r2c: complex output; c2r: reinterpret as double*
     const double2 *tw;   // generic kernel: tw[m] = exp(-2 pi i m / L), m in [0, L)
                          // pow2 kernel: stage-major table, see pow2_twiddle_count()
+    const double2 *tw2;  // real-transform kernel: tw2[k] = exp(-2 pi i k / N), k in [0, N/2)
     int64_t outer;       // number of (L x inner) planes
     int64_t inner;       // stride between consecutive points of a line, in elements
     int64_t in_plane;    // elements between consecutive planes of the input (== L*inner unless sub-viewed)
@@ -413,6 +414,108 @@ __global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS, Pow2Tile<L, 
 fft_pow2_kernel(const FftPassArgs a) {
     extern __shared__ double2 sm[];
     fft_pow2_tile<L, C, STRIDED, false>(a, blockIdx.x, sm);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Real transforms of even power-of-two length N = 2H on the last axis, as ONE complex transform of length H
+// (the packing trick: z[j] = x[2j] + i x[2j+1], which is exactly how a real line reads when viewed as double2):
+//   r2c   Z = FFT_H(z);  X[k] = (Z[k] + conj Z[H-k])/2 - (i/2) w^k (Z[k] - conj Z[H-k]),  w = e^{-2 pi i/N},
+//         k = 0..H-1, and X[H] = Re Z[0] - Im Z[0]; partners meet through one more shared-memory exchange.
+//   c2r   Z'[k] = (X[k] + conj X[H-k]) + i w^{-k} (X[k] - conj X[H-k]);  (x[2j], x[2j+1]) = IFFT_H(Z')[j]
+//         (the factor 2 of Z' = 2Z is the H-vs-N normalisation; `scale` carries 1/N as before).
+// Half the butterflies, half the shared memory and no padding loads compared with transforming a full complex
+// line per real line (what JavaFftService.rfft does on the CPU: JavaFftService.java:53-64). FUSE adds the fused
+// convolution's product-on-load and crop-on-store (FftPassArgs::mul / crop_cols).
+// ---------------------------------------------------------------------------------------------------------
+template <int H, int C, bool FUSE>
+__global__ void __launch_bounds__(Pow2Tile<H, C, false>::THREADS, Pow2Tile<H, C, false>::MIN_CTAS)
+fft_real_pow2_kernel(const FftPassArgs a) {
+    extern __shared__ double2 sm[];
+    using Stages = Pow2Stages<H, C, false, 1>;
+    constexpr int T = H / 8;
+    const int tid = threadIdx.x, t = tid % T, c = tid / T;
+    const int64_t line = (int64_t) blockIdx.x * C + c;
+    const bool active = line < a.outer;
+    const double2 *__restrict__ tw2 = a.tw2;  // tw2[k] = exp(-2 pi i k / (2H)), k in [0, H)
+    const double s = a.scale;
+    double2 v[8];
+    if (a.mode == MODE_R2C) {
+        const double2 *zin = reinterpret_cast<const double2 *>(reinterpret_cast<const double *>(a.in) + line * (2 * H));
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            v[m] = active ? zin[t + m * T] : make_double2(0.0, 0.0);
+        }
+        Stages::run(v, t, c, sm, a.tw);
+        __syncthreads();  // the last exchange of the stages has been read by everyone
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            sm[Stages::sidx(t + m * T, c)] = v[m];
+        }
+        __syncthreads();
+        if (!active) {
+            return;
+        }
+        double2 *hout = a.out + line * (H + 1);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int k = t + m * T;
+            const double2 zp = sm[Stages::sidx((H - k) & (H - 1), c)], w = __ldg(&tw2[k]);
+            const double ex = 0.5 * (v[m].x + zp.x), ey = 0.5 * (v[m].y - zp.y);  // (Z + conj Zp) / 2
+            const double ox = 0.5 * (v[m].y + zp.y), oy = -0.5 * (v[m].x - zp.x);  // (-i/2) (Z - conj Zp)
+            hout[k] = make_double2((ex + (ox * w.x - oy * w.y)) * s, (ey + (ox * w.y + oy * w.x)) * s);
+        }
+        if (t == 0) {
+            hout[H] = make_double2((v[0].x - v[0].y) * s, 0.0);
+        }
+    } else {  // MODE_C2R
+        const int64_t hoff = (FUSE && a.crop_cols > 0 ? crop_source_line(a, line) : line) * (H + 1);
+        if (active) {
+            const double2 *hin = a.in + hoff;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int k = t + m * T;
+                double2 x = hin[k], xp = hin[H - k];
+                if (FUSE && a.mul) {
+                    x = cmul(x, a.mul[hoff + k]);
+                    xp = cmul(xp, a.mul[hoff + H - k]);
+                }
+                const double2 w = __ldg(&tw2[k]);
+                const double sx = x.x + xp.x, sy = x.y - xp.y;  // X + conj Xp
+                const double dx = x.x - xp.x, dy = x.y + xp.y;  // X - conj Xp
+                // i * conj(w) * d = i * (w.x - i w.y) * (dx + i dy)
+                const double px = w.x * dx + w.y * dy, py = w.x * dy - w.y * dx;  // conj(w) * d
+                v[m] = make_double2(sy + px, sx - py);  // swap(Z'), Z' = (sx - py, sy + px): backward via the swap identity
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                v[m] = make_double2(0.0, 0.0);
+            }
+        }
+        Stages::run(v, t, c, sm, a.tw);
+        if (!active) {
+            return;
+        }
+        if (FUSE && a.crop_cols > 0) {
+            double *rout = reinterpret_cast<double *>(a.out) + line * a.crop_cols;
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                const int j = 2 * (t + m * T);
+                if (j < a.crop_cols) {
+                    rout[j] = v[m].y * s;
+                }
+                if (j + 1 < a.crop_cols) {
+                    rout[j + 1] = v[m].x * s;
+                }
+            }
+        } else {
+            double2 *zout = reinterpret_cast<double2 *>(reinterpret_cast<double *>(a.out) + line * (2 * H));
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                zout[t + m * T] = make_double2(v[m].y * s, v[m].x * s);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

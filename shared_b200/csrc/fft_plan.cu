@@ -98,6 +98,23 @@ static const double2 *pow2_twiddles_for(int L) {
     return upload_table(-L, host);
 }
 
+// Post-/pre-processing table of the packed real transforms: tw2[k] = exp(-2 pi i k / N), k in [0, N/2).
+static const double2 *real_twiddles_for(int N) {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    const int key = N + (1 << 28);
+    auto it = g_tw_cache.find(std::make_pair(dev, key));
+    if (it != g_tw_cache.end()) {
+        return it->second;
+    }
+    std::vector<double2> host((size_t) N / 2);
+    for (int k = 0; k < N / 2; k++) {
+        host[(size_t) k] = unit_root(k, N);
+    }
+    return upload_table(key, host);
+}
+
 // ---- axis-pass dispatch ------------------------------------------------------------------------------
 
 constexpr int strided_cols(int L) { return L <= 64 ? 32 : L <= 256 ? 16 : L <= 512 ? 8 : L <= 1024 ? 4 : 2; }
@@ -172,6 +189,56 @@ static void launch_pow2_L(const FftPassArgs &a, bool strided, cudaStream_t strea
     } else {
         constexpr int C = contig_lines(L);
         launch_pow2<L, C, false>(a, (a.outer + C - 1) / C, stream);
+    }
+}
+
+// Packed real transforms (r2c / c2r of even power-of-two length N = 2H, 32 <= N <= 8192).
+template <int H, bool FUSE>
+static void launch_real_H(const FftPassArgs &a, cudaStream_t stream) {
+    constexpr int C = contig_lines(H);
+    using Tile = Pow2Tile<H, C, false>;
+    static std::once_flag once[16];
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    if (Tile::SMEM_BYTES > 48 * 1024) {
+        std::call_once(once[dev & 15], [] {
+            SSTC_CUDA(cudaFuncSetAttribute(fft_real_pow2_kernel<H, C, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                    Tile::SMEM_BYTES));
+        });
+    }
+    const int64_t grid = (a.outer + C - 1) / C;
+    if (grid > kMaxGrid) {
+        throw std::runtime_error("FFT batch too large for one launch");
+    }
+    fft_real_pow2_kernel<H, C, FUSE><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
+    check_launch("fft_real_pow2_kernel");
+}
+
+template <int H>
+static void launch_real(const FftPassArgs &a, cudaStream_t stream) {
+    if (a.mul || a.crop_cols > 0) {
+        launch_real_H<H, true>(a, stream);
+    } else {
+        launch_real_H<H, false>(a, stream);
+    }
+}
+
+static bool real_kernel_holds(int N) { return (N & (N - 1)) == 0 && N >= 32 && N <= 8192; }
+
+static void dispatch_real(FftPassArgs &a, int N, cudaStream_t stream) {
+    a.tw = pow2_twiddles_for(N / 2);
+    a.tw2 = real_twiddles_for(N);
+    switch (N / 2) {
+    case 16: launch_real<16>(a, stream); break;
+    case 32: launch_real<32>(a, stream); break;
+    case 64: launch_real<64>(a, stream); break;
+    case 128: launch_real<128>(a, stream); break;
+    case 256: launch_real<256>(a, stream); break;
+    case 512: launch_real<512>(a, stream); break;
+    case 1024: launch_real<1024>(a, stream); break;
+    case 2048: launch_real<2048>(a, stream); break;
+    case 4096: launch_real<4096>(a, stream); break;
+    default: throw std::runtime_error("internal: real transform length");
     }
 }
 
@@ -251,7 +318,11 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     if (outer <= 0 || inner <= 0 || L <= 0) {
         return;
     }
-    if (!tile_kernels_hold(L)) {
+    // real transforms of power-of-two length: the packed half-length kernel (inputs / outputs are read as double2)
+    const bool packed_real = mode != MODE_C2C && real_kernel_holds(L) && inner == 1 && bin.n == 0 && bout.n == 0 && !layout &&
+            (mode == MODE_R2C ? !inverse : inverse) && !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) &&
+            !(fuse && fuse->mul && (reinterpret_cast<uintptr_t>(fuse->mul) & 15));
+    if (!packed_real && !tile_kernels_hold(L)) {
         // lengths the shared-memory kernels cannot hold: four-step (powers of two) or Bluestein (anything else)
         if (bin.n > 0 || bout.n > 0 || layout || fuse) {
             throw std::runtime_error("blocked / strided layouts need an axis length the tile kernels hold");
@@ -263,7 +334,8 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.in = static_cast<const double2 *>(in);
     a.out = static_cast<double2 *>(out);
     const bool pow2 = L >= 8 && L <= 4096 && (L & (L - 1)) == 0;
-    a.tw = pow2 ? pow2_twiddles_for(L) : twiddles_for(L);
+    a.tw = packed_real ? nullptr : pow2 ? pow2_twiddles_for(L) : twiddles_for(L);
+    a.tw2 = nullptr;
     a.outer = outer;
     a.inner = inner;
     a.in_plane = (int64_t) L * inner;
@@ -315,6 +387,10 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
                 a.blk[q] = static_cast<double2 *>(bout.ptrs[q]);
             }
         }
+    }
+    if (packed_real) {
+        dispatch_real(a, L, stream);
+        return;
     }
     // blocked addressing lives in the STRIDED kernels; inner == 1 is routed there as a 1-column plane
     const bool strided = inner > 1 || bin.n > 0 || bout.n > 0 || layout;
@@ -619,6 +695,10 @@ static void build_plan(sstc_fft_plan_s &p) {
     // Build every twiddle table now so execute() never allocates.
     for (const Step &s : p.steps) {
         const int L = s.axis_len;
+        if (s.mode != MODE_C2C && real_kernel_holds(L)) {
+            pow2_twiddles_for(L / 2);
+            real_twiddles_for(L);
+        }
         if (L >= 8 && L <= 4096 && (L & (L - 1)) == 0) {
             pow2_twiddles_for(L);
         } else if (L <= kGenericMaxL && (L & (L - 1)) != 0) {
