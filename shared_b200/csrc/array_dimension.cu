@@ -677,12 +677,128 @@ __global__ void __launch_bounds__(kThreads) index_lines_thread_kernel(const doub
     }
 }
 
+// Warp per line, for many lines along the fastest dimension: no CTA barrier, no shared memory. Pass 1 (MAX / MIN
+// only) folds the line with 8 loads in flight per lane; pass 2 re-reads it (it is 16*len bytes per warp and comes
+// back from L2), ballots the matches of every 32-point step and writes their positions in ascending order behind
+// a running count; the tail is filled with -1 (DimensionOps.java:186-199).
+template <int OP>
+__global__ void __launch_bounds__(kThreads) index_lines_warp_kernel(const double *__restrict__ in, int32_t *out,
+        Lines L) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = (((int64_t) blockIdx.x * blockDim.x) + threadIdx.x) >> 5; m < L.n_lines; m += warps) {
+        int64_t ioff, ooff;
+        line_base(L, m, ioff, ooff);
+        double ext = 0.0;
+        int pos = 0;
+        bool need_scan = true;
+        if (OP == RI_MAX || OP == RI_MIN) {
+            // Every lane tracks, per accumulator, its extreme, where it first saw it and how often. If the line's
+            // extreme occurs once (the usual case for real-valued data) its position is known after this one pass.
+            double best[8];
+            int first[8], cnt[8];
+            bool nan = false;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                best[e] = OP == RI_MAX ? -DBL_MAX : DBL_MAX;
+                first[e] = 0x7fffffff;
+                cnt[e] = 0;
+            }
+            auto better = [](double x, double y) { return OP == RI_MAX ? x > y : x < y; };
+            auto take = [&](int e, double x, int j) {
+                nan |= x != x;
+                if (better(x, best[e])) {
+                    best[e] = x;
+                    first[e] = j;
+                    cnt[e] = 1;
+                } else if (x == best[e]) {
+                    first[e] = first[e] < j ? first[e] : j;
+                    cnt[e]++;
+                }
+            };
+            int64_t j = lane;
+            for (; j + 7 * 32 < L.len; j += 8 * 32) {
+                double x[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    x[e] = in[ioff + (j + e * 32) * L.ilstride];
+                }
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    take(e, x[e], (int) j + e * 32);
+                }
+            }
+            for (; j < L.len; j += 32) {
+                take(0, in[ioff + j * L.ilstride], (int) j);
+            }
+            auto merge = [&](double &b0, int &f0, int &c0, double b1, int f1, int c1) {
+                if (better(b1, b0)) {
+                    b0 = b1;
+                    f0 = f1;
+                    c0 = c1;
+                } else if (b1 == b0) {
+                    f0 = f0 < f1 ? f0 : f1;
+                    c0 += c1;
+                }
+            };
+#pragma unroll
+            for (int e = 1; e < 8; e++) {
+                merge(best[0], first[0], cnt[0], best[e], first[e], cnt[e]);
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                const double b1 = __shfl_xor_sync(0xffffffffu, best[0], off);
+                const int f1 = __shfl_xor_sync(0xffffffffu, first[0], off);
+                const int c1 = __shfl_xor_sync(0xffffffffu, cnt[0], off);
+                merge(best[0], first[0], cnt[0], b1, f1, c1);
+            }
+            ext = best[0];
+            if (__any_sync(0xffffffffu, nan)) {
+                need_scan = false;  // Math.max / Math.min give NaN, and nothing equals NaN: no positions
+            } else if (cnt[0] == 1) {
+                if (lane == 0) {
+                    out[ooff] = first[0];
+                }
+                pos = 1;
+                need_scan = false;
+            } else if (cnt[0] == 0) {
+                // nothing beat the start value -/+Double.MAX_VALUE (the line holds only -/+infinity): positions are
+                // those equal to the start value, as the reference's fold leaves it (Arithmetic.java:54,72) -> none
+                need_scan = true;
+            }
+        }
+        for (int64_t base = 0; need_scan && base < L.len; base += 8 * 32) {
+            double x[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int64_t j = base + e * 32 + lane;
+                x[e] = j < L.len ? in[ioff + j * L.ilstride] : 0.0;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int64_t j = base + e * 32 + lane;
+                const bool hit = j < L.len && ri_pred<OP>(x[e], ext);
+                const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    out[ooff + (int64_t) (pos + __popc(ballot & ((1u << lane) - 1u))) * L.olstride] = (int32_t) j;
+                }
+                pos += __popc(ballot);
+            }
+        }
+        for (int64_t j = pos + lane; j < L.len; j += 32) {
+            out[ooff + j * L.olstride] = -1;
+        }
+    }
+}
+
 template <int OP>
 static void index_dim(const double *in, int32_t *out, const Lines &L, cudaStream_t s) {
     if (L.n_lines == 0 || L.len == 0) {
         return;
     }
-    if (line_is_fastest(L) && L.len >= 64) {
+    if (line_is_fastest(L) && L.len >= 64 && L.n_lines >= (int64_t) sm_count() * 32 && L.len <= 2147483647LL) {
+        const int64_t blocks = (L.n_lines * 32 + kThreads - 1) / kThreads;
+        index_lines_warp_kernel<OP><<<(int) std::min<int64_t>(blocks, (int64_t) sm_count() * 16), kThreads, 0, s>>>(in, out, L);
+    } else if (line_is_fastest(L) && L.len >= 64) {
         int grid = (int) std::min<int64_t>(L.n_lines, (int64_t) sm_count() * 16);
         constexpr int kCacheMax = 12288;  // 96 KB of shared memory: two lines resident per SM
         if (L.len <= kCacheMax && (OP == RI_MAX || OP == RI_MIN)) {

@@ -175,6 +175,38 @@ def test_riop_matches_reference(k, dims, order):
     assert np.array_equal(ties, np.sort(src))
 
 
+def test_riop_many_lines_edge_cases(k):
+    """The warp-per-line index kernel (many lines along the fastest dimension): unique extreme (one pass), ties
+    (second pass), NaN (Math.max gives NaN, nothing equals it), a line of -infinity (the fold starts from
+    -Double.MAX_VALUE: DimensionOps.java:181), against the definition."""
+    rng = np.random.default_rng(21)
+    rows, n = 5000, 96
+    src = rng.uniform(-1, 1, rows * n)
+    m = src.reshape(rows, n)
+    m[1, :] = np.round(m[1, :] * 2)          # ties
+    m[2, 7] = np.nan
+    m[3, :] = -np.inf
+    m[4, :] = 0.25                           # every position matches
+    m[5, 40] = np.inf
+    for op, red, start in (("RI_MAX", np.max, -np.finfo(np.float64).max), ("RI_MIN", np.min, np.finfo(np.float64).max)):
+        if op == "RI_MIN":
+            m[3, :] = np.inf
+            m[5, 40] = -np.inf
+        out = np.full(rows * n, -9, dtype=np.int32)
+        k.riOp(OP[op], src.copy(), [rows, n], [n, 1], out, 1)
+        out = out.reshape(rows, n)
+        for r in range(rows):
+            line = m[r]
+            if np.isnan(line).any():
+                want = []
+            else:
+                ext = red(np.append(line, start))
+                want = list(np.nonzero(line == ext)[0])
+            exp = np.full(n, -1, dtype=np.int32)
+            exp[:len(want)] = want
+            assert np.array_equal(out[r], exp), (op, r)
+
+
 @needs_ref
 @pytest.mark.parametrize("dims,order", SHAPES, ids=lambda v: "x".join(map(str, v)) if isinstance(v, list) else v)
 def test_rdop_matches_reference(k, dims, order):

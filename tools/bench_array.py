@@ -57,7 +57,7 @@ cases += [
     ("rdOp SUM dim1", 16 * N, lambda: dk.rdOp(OP["RD_SUM"], P, N, [n, n], far, z.data_ptr(), N, 1)),
     ("rdOp SUM dim0", 16 * N, lambda: dk.rdOp(OP["RD_SUM"], P, N, [n, n], far, z.data_ptr(), N, 0)),
     ("rdOp SUM dims 0,1", 32 * N, lambda: dk.rdOp(OP["RD_SUM"], P, N, [n, n], far, z.data_ptr(), N, 0, 1)),
-    ("riOp MAX dim1", 20 * N, lambda: dk.riOp(OP["RI_MAX"], P, N, [n, n], far, idx.data_ptr(), N, 1)),
+    ("riOp MAX dim1 (12 B/elt: SURVEY 8d)", 12 * N, lambda: dk.riOp(OP["RI_MAX"], P, N, [n, n], far, idx.data_ptr(), N, 1)),
     ("map transpose", 16 * N, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], [1, n])),
     ("map copy", 16 * N, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], far)),
 ]
