@@ -236,12 +236,21 @@ __global__ void __launch_bounds__(kThreads) reduce_lines_thread_kernel(const dou
     const int64_t lo = sp * chunk, hi = lo + chunk < L.len ? lo + chunk : L.len;
     const double mu = SQ ? mean[ooff] : 0.0;
     double acc = rr_identity<OP>();
+    bool nan = false;
     for (int64_t j = lo; j < hi; j++) {
         double x = in[ioff + j * L.ilstride];
         if (SQ) {
             x = (x - mu) * (x - mu);
         }
-        acc = rr_combine<OP>(acc, x);
+        if (OP == RR_MAX || OP == RR_MIN) {  // NaN-ignoring fold + NaN flag, as in fold_line
+            nan |= x != x;
+            acc = OP == RR_MAX ? fmax(acc, x) : fmin(acc, x);
+        } else {
+            acc = rr_combine<OP>(acc, x);
+        }
+    }
+    if ((OP == RR_MAX || OP == RR_MIN) && nan) {
+        acc = __longlong_as_double(0x7ff8000000000000LL);
     }
     if (splits == 1) {
         out[ooff] = divisor != 0.0 ? acc / divisor : acc;

@@ -175,6 +175,25 @@ def test_riop_matches_reference(k, dims, order):
     assert np.array_equal(ties, np.sort(src))
 
 
+def test_rrop_max_min_nan_and_zero_semantics(k):
+    """Math.max / Math.min (DimensionOps.java:96-123): a NaN anywhere along the line gives NaN; the folds start from
+    -/+Double.MAX_VALUE, so a line of -infinity reduces to -MAX_VALUE under MAX."""
+    rng = np.random.default_rng(22)
+    for dims in ([6, 300], [300, 6], [5000, 70], [3, 4096]):
+        n = int(np.prod(dims))
+        src = rng.uniform(-1, 1, n)
+        m = src.reshape(dims)
+        m[1, 3] = np.nan
+        m[2, :] = -np.inf
+        for dim in (0, 1):
+            ddims = [1 if i == dim else dims[i] for i in range(2)]
+            for op, red, start in (("RR_MAX", np.max, -np.finfo(np.float64).max), ("RR_MIN", np.min, np.finfo(np.float64).max)):
+                dst = np.zeros(int(np.prod(ddims)))
+                k.rrOp(OP[op], src.copy(), dims, strides(dims), dst, ddims, strides(ddims), dim)
+                want = red(np.concatenate([m, np.full(ddims, start)], axis=dim), axis=dim).ravel()
+                assert np.array_equal(dst, want, equal_nan=True), (dims, dim, op)
+
+
 def test_riop_many_lines_edge_cases(k):
     """The warp-per-line index kernel (many lines along the fastest dimension): unique extreme (one pass), ties
     (second pass), NaN (Math.max gives NaN, nothing equals it), a line of -infinity (the fold starts from
