@@ -228,6 +228,22 @@ int sstc_mul_dev(const double *lhs, int64_t nl, const double *rhs, int64_t nr, i
 int sstc_diag(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex);
 int sstc_diag_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, int complex, void *stream);
 
+/* invert (Bindings.cpp:139-142 -> LinearAlgebraOpsLu.cpp:26-76): dst = src^-1 for a row-major size x size matrix, by
+ * LU with partial pivoting (JAMA's pivot rule). "Matrix is singular" when U has a zero on its diagonal. dst is
+ * overwritten (the reference assumes it arrives zero-filled). The device twin synchronises `stream` once. */
+int sstc_invert(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size);
+int sstc_invert_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, void *stream);
+
+/* find (Bindings.cpp:160-163 -> IndexOps.cpp:26-130): `logical` holds one index per dimension with exactly one -1
+ * marking the active dimension; along that line of the int array (as riOp writes it: positions, then -1 padding)
+ * *count = number of non-negative entries, and out[0 .. *count) = the first *count entries of the line. `out` must
+ * hold a whole line (sD[active] ints; host tier: nout says how many it holds). The device twin takes device
+ * `src` / `out`, writes *count on the host and synchronises `stream`. */
+int sstc_find(const int32_t *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, const int32_t *logical,
+        int32_t *out, int64_t nout, int32_t *count);
+int sstc_find_dev(const int32_t *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, const int32_t *logical,
+        int32_t *out, int32_t *count, void *stream);
+
 /* ---- ImageKernel ------------------------------------------------------------------------------------
  *
  * The reference library's second native service (org.shared.image.kernel.ImageKernel,

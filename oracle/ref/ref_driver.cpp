@@ -169,6 +169,33 @@ int sstref_diag(const double *src, int nsrc, double *dst, int ndst, int size, in
     return env_done(env);
 }
 
+int sstref_invert(const double *src, int nsrc, double *dst, int ndst, int size) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), d = DARR(dst, ndst);
+    LinearAlgebraOps::invert(env, 0, &s, &d, size);
+    return env_done(env);
+}
+
+/* returns the length of the result (copied into out, capacity cap), or -1 on a Java exception */
+int sstref_find(const int *src, int nsrc, const int *sD, const int *sS, int nd, const int *logical, int *out, int cap) {
+    JNIEnv *env = env_get();
+    _jobject s = IARR(src, nsrc), sd = IARR(sD, nd), ss = IARR(sS, nd), lg = IARR(logical, nd);
+    jintArray res = IndexOps::find(env, 0, &s, &sd, &ss, &lg);
+    int n = -1;
+    if (!env->pending && res) {
+        n = res->len;
+        for (int i = 0; i < n && i < cap; i++) {
+            out[i] = ((int *) res->data)[i];
+        }
+    }
+    if (res) {
+        free(res->data);
+        free(res);
+    }
+    env_done(env);
+    return n;
+}
+
 /* NativeImageKernel (Bindings.cpp:144-158) */
 int sstref_integral_image(const double *src, int nsrc, const int *sD, const int *sS, double *dst, int ndst,
         const int *dD, const int *dS, int nd) {

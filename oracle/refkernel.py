@@ -128,6 +128,20 @@ class RefKernel:
         self._chk(self._l.sstref_diag(_p(_f64(srcV)), srcV.size, _p(_f64(dstV)), dstV.size, int(size),
                                       int(bool(complex_))))
 
+    def invert(self, srcV, dstV, size):
+        self._chk(self._l.sstref_invert(_p(_f64(srcV)), srcV.size, _p(_f64(dstV)), dstV.size, int(size)))
+
+    def find(self, srcV, srcD, srcS, logical):
+        sD, sS, lg = _i32(srcD), _i32(srcS), _i32(logical)
+        assert srcV.dtype == np.int32
+        if not (sD.size == sS.size == lg.size):
+            raise RefKernelError("Invalid arguments")
+        out = np.empty(max(1, srcV.size), dtype=np.int32)
+        n = self._l.sstref_find(_p(srcV), srcV.size, _p(sD), _p(sS), sD.size, _p(lg), _p(out), out.size)
+        if n < 0:
+            raise RefKernelError(self._l.sstref_last_error().decode())
+        return out[:n].copy()
+
     # -- ImageKernel (src/org/shared/image/kernel/ImageKernel.java:56-80) -------------------------------------
     def createIntegralImage(self, srcV, srcD, srcS, dstV, dstD, dstS):
         sD, sS, dD, dS = _i32(srcD), _i32(srcS), _i32(dstD), _i32(dstS)

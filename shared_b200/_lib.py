@@ -82,6 +82,10 @@ for _name, _args in _ARRAY_OPS.items():
     SIGNATURES[_name] = (ctypes.c_int, _args)
     SIGNATURES[_name + "_dev"] = (ctypes.c_int, _args + [ctypes.c_void_p])  # device twin: same arguments + stream
 SIGNATURES["sstc_srand"] = (ctypes.c_int, [ctypes.c_uint64])
+SIGNATURES["sstc_invert"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _i])
+SIGNATURES["sstc_invert_dev"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _i, _vp])
+SIGNATURES["sstc_find"] = (ctypes.c_int, [_vp, _i64, c_i32_p, c_i32_p, _i, c_i32_p, _vp, _i64, c_i32_p])
+SIGNATURES["sstc_find_dev"] = (ctypes.c_int, [_vp, _i64, c_i32_p, c_i32_p, _i, c_i32_p, _vp, c_i32_p, _vp])
 _IMAGE_OPS = {
     "sstc_integral_image": [_vp, _i64, c_i32_p, c_i32_p, _vp, _i64, c_i32_p, c_i32_p, _i],
     "sstc_integral_histogram": [_vp, _i64, c_i32_p, c_i32_p, _i, _vp, _i64, _vp, _i64, c_i32_p, c_i32_p],

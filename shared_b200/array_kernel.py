@@ -152,11 +152,29 @@ class CudaArrayKernel:
     def diag(self, srcV, dstV, size, complex_):
         _lib.check(self._l.sstc_diag(_vp(srcV), srcV.size, _vp(dstV), dstV.size, int(size), int(bool(complex_))))
 
+    def invert(self, srcV, dstV, size):
+        """ArrayKernel.invert (ArrayKernel.java:576-586; LinearAlgebraOpsLu.cpp:26-76)."""
+        _lib.check(self._l.sstc_invert(_vp(srcV), srcV.size, _vp(dstV), dstV.size, int(size)))
+
+    def find(self, srcV, srcD, srcS, logical):
+        """ArrayKernel.find (ArrayKernel.java:603; IndexOps.java:44-91): returns a new int32 array."""
+        if srcV.dtype != np.int32:
+            raise _lib.SstCudaError("Invalid array types")
+        sD, sS, lg = _i32(srcD), _i32(srcS), _i32(logical)
+        if not (sD.size == sS.size == lg.size):
+            raise _lib.SstCudaError("Invalid arguments")
+        active = [d for d in range(lg.size) if lg[d] == -1]
+        line = np.empty(int(sD[active[0]]) if len(active) == 1 else 0, dtype=np.int32)
+        count = ctypes.c_int32()
+        _lib.check(self._l.sstc_find(_vp(srcV), srcV.size, _pi(sD), _pi(sS), sD.size, _pi(lg), _vp(line), line.size,
+                                     ctypes.byref(count)))
+        return line[:count.value].copy()
+
     # -- outside the north-star op families (SURVEY.md section 8, row b15) --------------------------------------------
     def _unsupported(self, *args, **kwargs):
         raise NotImplementedError("not provided by the CUDA ArrayKernel (no CPU fallback)")
 
-    svd = eigs = invert = find = insertSparse = sliceSparse = _unsupported
+    svd = eigs = insertSparse = sliceSparse = _unsupported
 
 
 class DeviceArrayKernel:

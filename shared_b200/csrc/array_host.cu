@@ -270,4 +270,40 @@ int sstc_integral_histogram(const double *src, int64_t nsrc, const int32_t *sD, 
     });
 }
 
+// ---- invert / find (Bindings.cpp:139-142, 160-163) --------------------------------------------------------------
+
+int sstc_invert(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size) {
+    return guarded([&] {
+        if (nsrc < 0 || ndst < 0 || (nsrc > 0 && !src) || (ndst > 0 && !dst)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        Staged s0(0, src, nsrc * 8, true), d(1, dst, ndst * 8, false);
+        rethrow(sstc_invert_dev(static_cast<const double *>(s0.dev), nsrc, static_cast<double *>(d.dev), ndst, size,
+                nullptr));
+        d.download();
+        finish();
+    });
+}
+
+int sstc_find(const int32_t *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, const int32_t *logical,
+        int32_t *out, int64_t nout, int32_t *count) {
+    return guarded([&] {
+        if (nsrc < 0 || nout < 0 || (nsrc > 0 && !src) || (nout > 0 && !out) || !count) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        Staged s0(0, src, nsrc * 4, true), d(1, out, nout * 4, false);
+        for (int i = 0; i < nd && sD && logical; i++) {
+            if (logical[i] == -1 && nout < sD[i]) {
+                throw std::runtime_error("Invalid arguments");  // `out` must hold a whole line
+            }
+        }
+        rethrow(sstc_find_dev(static_cast<const int32_t *>(s0.dev), nsrc, sD, sS, nd, logical,
+                static_cast<int32_t *>(d.dev), count, nullptr));
+        if (*count > 0) {
+            SSTC_CUDA(cudaMemcpyAsync(out, d.dev, (size_t) *count * 4, cudaMemcpyDeviceToHost, 0));
+        }
+        finish();
+    });
+}
+
 }  // extern "C"

@@ -511,6 +511,49 @@ JNIEXPORT void JNICALL AK(diag)(JNIEnv *env, jobject, jdoubleArray srcV, jdouble
     raise_last(env, rc);
 }
 
+JNIEXPORT void JNICALL AK(invert)(JNIEnv *env, jobject, jdoubleArray srcV, jdoubleArray dstV, jint size) {
+    if (!srcV || !dstV) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize ns = len(env, srcV), nd = len(env, dstV);
+    int rc;
+    {
+        Pin s(env, srcV, true), d(env, dstV, false);
+        rc = sstc_invert(s.as<double>(), ns, d.as<double>(), nd, size);
+    }
+    raise_last(env, rc);
+}
+
+JNIEXPORT jintArray JNICALL AK(find)(JNIEnv *env, jobject, jintArray srcV, jintArray srcD, jintArray srcS,
+        jintArray logical) {
+    if (!srcV || !srcD || !srcS || !logical) {
+        raise(env, "Invalid arguments");
+        return nullptr;
+    }
+    const jsize ns = len(env, srcV), rank = len(env, srcD);
+    if (rank != len(env, srcS) || rank != len(env, logical)) {
+        raise(env, "Invalid arguments");
+        return nullptr;
+    }
+    std::vector<int32_t> line((size_t) (ns > 0 ? ns : 1));  // a line is never longer than the array
+    int32_t count = 0;
+    int rc;
+    {
+        Pin s(env, srcV, true), sd(env, srcD, true), ss(env, srcS, true), lg(env, logical, true);
+        rc = sstc_find(s.as<int32_t>(), ns, sd.as<int32_t>(), ss.as<int32_t>(), rank, lg.as<int32_t>(), line.data(),
+                (int64_t) line.size(), &count);
+    }
+    if (rc != 0) {
+        raise_last(env, rc);
+        return nullptr;
+    }
+    jintArray res = env->NewIntArray(count);  // IndexOps.cpp:38 (Common::newIntArray)
+    if (res && count > 0) {
+        env->SetIntArrayRegion(res, 0, count, reinterpret_cast<const jint *>(line.data()));
+    }
+    return res;
+}
+
 // ---- ImageKernel (Bindings.cpp:144-158 -> NativeImageKernel.cpp:32-247) --------------------------------------------
 
 JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaImageKernel_createIntegralImage(JNIEnv *env, jobject,

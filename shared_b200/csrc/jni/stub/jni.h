@@ -50,6 +50,8 @@ struct JNIEnv_ {
     void ReleasePrimitiveArrayCritical(jarray array, void *carray, jint mode);
     jdoubleArray NewDoubleArray(jsize len);
     void SetDoubleArrayRegion(jdoubleArray array, jsize start, jsize len, const jdouble *buf);
+    jintArray NewIntArray(jsize len);
+    void SetIntArrayRegion(jintArray array, jsize start, jsize len, const jint *buf);
     jobject GetObjectArrayElement(jobjectArray array, jsize index);
     void SetObjectArrayElement(jobjectArray array, jsize index, jobject val);
     jfieldID GetStaticFieldID(jclass clazz, const char *name, const char *sig);

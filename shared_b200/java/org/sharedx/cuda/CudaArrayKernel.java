@@ -10,8 +10,8 @@
  *
  * The sixteen operations on the FFT / array-kernel hot path are native (JNI glue:
  * shared_b200/csrc/jni/jni_glue.cpp, one export per method, same signatures as NativeArrayKernel.java:56-154).
- * The six interface members outside that path (svd, eigs, invert, find, insertSparse, sliceSparse) throw
- * {@link UnsupportedOperationException}: this provider has no CPU fallback.
+ * Of the interface members outside that path, invert and find are provided; svd, eigs, insertSparse and
+ * sliceSparse throw {@link UnsupportedOperationException}: this provider has no CPU fallback.
  */
 package org.sharedx.cuda;
 
@@ -103,15 +103,13 @@ public class CudaArrayKernel implements ArrayKernel {
         throw new UnsupportedOperationException("eigs is not provided by the CUDA ArrayKernel");
     }
 
+    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_invert -> sstc_invert (LU with partial pivoting on the GPU). */
     @Override
-    public void invert(double[] srcV, double[] dstV, int size) {
-        throw new UnsupportedOperationException("invert is not provided by the CUDA ArrayKernel");
-    }
+    final public native void invert(double[] srcV, double[] dstV, int size);
 
+    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_find -> sstc_find; the result array is allocated by the glue. */
     @Override
-    public int[] find(int[] srcV, int[] srcD, int[] srcS, int[] logical) {
-        throw new UnsupportedOperationException("find is not provided by the CUDA ArrayKernel");
-    }
+    final public native int[] find(int[] srcV, int[] srcD, int[] srcS, int[] logical);
 
     @Override
     public <V> SparseArrayState<V> insertSparse( //

@@ -400,6 +400,51 @@ def test_mul_matches_reference(k):
     k.mul(np.zeros(0), np.zeros(0), 0, 0, c, False)  # lr == 0 / rc == 0 are legal (MatrixOps.java:46-55)
 
 
+@needs_ref
+def test_invert_matches_reference(k):
+    rng = np.random.default_rng(31)
+    for n in (1, 2, 3, 17, 64, 128, 200):
+        a = rng.uniform(0, 1, (n, n)) + 2 * np.eye(n)  # MatrixTest.java:227-242 builds its inputs like this
+        if n >= 3:
+            a[[0, n - 1]] = a[[n - 1, 0]]              # force row exchanges
+        got, want = np.full(n * n, 7.0), np.zeros(n * n)
+        k.invert(a.ravel().copy(), got, n)
+        ref.invert(a.ravel().copy(), want, n)
+        assert np.abs(a @ got.reshape(n, n) - np.eye(n)).sum() < 1e-8, n  # the reference test's own criterion
+        assert rel(got, want) < 1e-11, (n, rel(got, want))
+    import shared_b200 as s
+    with pytest.raises(s.SstCudaError, match="Matrix is singular"):
+        k.invert(np.zeros(9), np.zeros(9), 3)
+    with pytest.raises(s.SstCudaError, match="Invalid arguments"):
+        k.invert(np.zeros(8), np.zeros(9), 3)
+    k.invert(np.zeros(0), np.zeros(0), 0)
+
+
+@needs_ref
+def test_find_matches_reference(k):
+    rng = np.random.default_rng(32)
+    for dims, order in (([7], "FAR"), ([5, 9], "FAR"), ([5, 9], "NEAR"), ([3, 4, 300], "FAR"), ([3, 4, 5], "NEAR")):
+        n = int(np.prod(dims))
+        src = rng.uniform(-1, 1, n)
+        idx = np.zeros(n, dtype=np.int32)
+        st = strides(dims, order)
+        for dim in range(len(dims)):
+            k.riOp(OP["RI_GZERO"], src.copy(), dims, st, idx, dim)  # positions of the positive entries, then -1
+            for _ in range(6):
+                logical = [int(rng.integers(0, d)) for d in dims]
+                logical[dim] = -1
+                got, want = k.find(idx, dims, st, logical), ref.find(idx, dims, st, logical)
+                assert got.dtype == np.int32 and np.array_equal(got, want), (dims, order, logical)
+    import shared_b200 as s
+    v = np.arange(8, dtype=np.int32)
+    with pytest.raises(s.SstCudaError, match="Invalid index"):
+        k.find(v, [2, 4], [4, 1], [2, -1])
+    with pytest.raises(s.SstCudaError, match="Invalid arguments"):
+        k.find(v, [2, 4], [4, 1], [-1, -1])
+    with pytest.raises(s.SstCudaError, match="Invalid dimensions and/or strides"):
+        k.find(v, [2, 4], [1, 1], [0, -1])
+
+
 def test_error_messages(k):
     import shared_b200 as s
     E = s.SstCudaError

@@ -51,3 +51,22 @@ def test_error_text():
         ref.rrOp(0, np.zeros(6), [2, 3], [1, 1], np.zeros(2), [2, 1], [1, 1], 1)
     with pytest.raises(oracle.refkernel.RefKernelError, match="Operation type not recognized"):
         ref.ruOp(99, 0.0, np.zeros(3))
+
+
+def test_invert_and_find_reference_properties():
+    # MatrixTest.java:227-242: (rnd + 2I) . inverse == I, sum |.| < 1e-8; "Matrix is singular" on a zero pivot
+    rng = np.random.default_rng(5)
+    n = 48
+    a = rng.uniform(0, 1, (n, n)) + 2 * np.eye(n)
+    inv = np.zeros(n * n)
+    ref.invert(a.ravel().copy(), inv, n)
+    assert np.abs(a @ inv.reshape(n, n) - np.eye(n)).sum() < 1e-8
+    with pytest.raises(oracle.refkernel.RefKernelError, match="Matrix is singular"):
+        ref.invert(np.zeros(9), np.zeros(9), 3)
+    # IndexOps.java:44-91 on a riOp-shaped array: positions, then -1 padding
+    v = np.array([3, 1, -1, -1, 0, 2, 5, -1], dtype=np.int32)
+    assert list(ref.find(v, [2, 4], [4, 1], [1, -1])) == [0, 2, 5]
+    assert list(ref.find(v, [2, 4], [4, 1], [0, -1])) == [3, 1]
+    assert list(ref.find(v, [2, 4], [4, 1], [-1, 3])) == []
+    with pytest.raises(oracle.refkernel.RefKernelError, match="Invalid index"):
+        ref.find(v, [2, 4], [4, 1], [2, -1])
