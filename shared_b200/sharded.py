@@ -161,10 +161,11 @@ class SlabFft3d:
             self.peer = [PeerBuffer(self.n_local, dev, group) for _ in range(2)]
             self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
             self.groups = next(g for g in (groups or 4, 4, 2, 1) if self.y_loc % g == 0)
-            # measured on 8 B200 (512^3): one exchange CTA per SM keeps NVLink busy (74 do not) and leaves room for the
-            # x pass to run beside it; an uncapped grid starves the x pass and loses the overlap (0.55 vs 0.51 ms)
-            self.exchange_ctas = (torch.cuda.get_device_properties(dev).multi_processor_count
-                                  if exchange_ctas is None else int(exchange_ctas))
+            # measured on B200s (512^3, tools/sweep_sharded.py): at 4 and 8 ranks one exchange CTA per SM keeps NVLink
+            # busy (74 do not) and leaves room for the x pass to run beside it (uncapped: 0.55 vs 0.51 ms at 8); at 2
+            # ranks the exchange pass moves half of the data and wants two per SM (1.40 vs 1.54 ms)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            self.exchange_ctas = (sms * (2 if self.world == 2 else 1)) if exchange_ctas is None else int(exchange_ctas)
             self.flags = PeerBuffer(16, dev, group)  # 8 uint64 epoch slots per rank (+ padding)
             self.flags.tensor.zero_()
             torch.cuda.synchronize(dev)
