@@ -56,13 +56,29 @@ struct RealUnary {
     }
 };
 
-template <class F>
+template <class F, int B>
 __global__ void __launch_bounds__(kThreads) real_map_kernel(double *__restrict__ v, int64_t n, F f) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
     const int64_t tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n2 = n >> 1;
     double2 *v2 = reinterpret_cast<double2 *>(v);
-    for (int64_t i = tid; i < n2; i += stride) {
+    // B independent 16-byte loads in flight per thread, then the maps: B = 4 for the long-latency ones (sqrt, exp,
+    // pow, ...: measured 0.76 -> 0.92 and 0.71 -> 0.86 of HBM at 8192^2), B = 1 for the one-instruction ones
+    int64_t i = tid;
+    for (; B > 1 && i + (B - 1) * stride < n2; i += B * stride) {
+        double2 x[B];
+#pragma unroll
+        for (int e = 0; e < B; e++) {
+            x[e] = v2[i + e * stride];
+        }
+#pragma unroll
+        for (int e = 0; e < B; e++) {
+            x[e].x = f(x[e].x, 2 * (i + e * stride));
+            x[e].y = f(x[e].y, 2 * (i + e * stride) + 1);
+            v2[i + e * stride] = x[e];
+        }
+    }
+    for (; i < n2; i += stride) {
         double2 x = v2[i];
         x.x = f(x.x, 2 * i);
         x.y = f(x.y, 2 * i + 1);
@@ -85,7 +101,8 @@ template <int OP>
 static void launch_real_unary(double a, double *v, int64_t n, cudaStream_t s) {
     RealUnary<OP> f{a, OP == RU_RND ? next_rng_key() : 0};
     if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
-        real_map_kernel<<<stream_grid(n, 2), kThreads, 0, s>>>(v, n, f);
+        constexpr bool light = OP == RU_ADD || OP == RU_MUL || OP == RU_ABS || OP == RU_SQR || OP == RU_FILL;
+        real_map_kernel<RealUnary<OP>, light ? 1 : 4><<<stream_grid(n, 2), kThreads, 0, s>>>(v, n, f);
     } else {
         scalar_map_kernel<<<stream_grid(n), kThreads, 0, s>>>(v, n, f);
     }
@@ -122,10 +139,22 @@ struct ComplexUnary {
     }
 };
 
-template <class F>
+template <class F, int B>
 __global__ void __launch_bounds__(kThreads) complex_map_kernel(double2 *__restrict__ v, int64_t n, F f) {
     const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (; B > 1 && i + (B - 1) * stride < n; i += B * stride) {  // B loads in flight ahead of the long-latency maps
+        double2 x[B];
+#pragma unroll
+        for (int e = 0; e < B; e++) {
+            x[e] = v[i + e * stride];
+        }
+#pragma unroll
+        for (int e = 0; e < B; e++) {
+            v[i + e * stride] = f(x[e], i + e * stride);
+        }
+    }
+    for (; i < n; i += stride) {
         v[i] = f(v[i], i);
     }
 }
@@ -148,7 +177,9 @@ template <int OP>
 static void launch_complex_unary(double re, double im, double *v, int64_t n_complex, cudaStream_t s) {
     ComplexUnary<OP> f{re, im, OP == CU_RND ? next_rng_key() : 0};
     if ((reinterpret_cast<uintptr_t>(v) & 15) == 0) {
-        complex_map_kernel<<<stream_grid(n_complex), kThreads, 0, s>>>(reinterpret_cast<double2 *>(v), n_complex, f);
+        constexpr bool light = OP == CU_ADD || OP == CU_MUL || OP == CU_CONJ || OP == CU_FILL;
+        complex_map_kernel<ComplexUnary<OP>, light ? 1 : 4><<<stream_grid(n_complex), kThreads, 0, s>>>(
+                reinterpret_cast<double2 *>(v), n_complex, f);
     } else {
         complex_map_unaligned_kernel<<<stream_grid(n_complex), kThreads, 0, s>>>(v, n_complex, f);
     }
