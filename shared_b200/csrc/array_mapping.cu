@@ -70,6 +70,23 @@ __global__ void __launch_bounds__(kThreads) map_rows_kernel(const T *__restrict_
         uint32_t j = j0 + threadIdx.x;
         uint32_t si = ((uint32_t) M.sstart[last] + j) % sdim, di = ((uint32_t) M.dstart[last] + j) % ddim;
         const uint32_t sstep = kThreads % sdim, dstep = kThreads % ddim;
+        for (; j + 3 * kThreads < j1; j += 4 * kThreads) {  // four loads in flight per thread
+            T x[4];
+            uint32_t dpos[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                x[e] = src[soff + (int64_t) si * ss];
+                dpos[e] = di;
+                si += sstep;
+                si = si >= sdim ? si - sdim : si;
+                di += dstep;
+                di = di >= ddim ? di - ddim : di;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                dst[doff + (int64_t) dpos[e] * ds] = x[e];
+            }
+        }
         for (; j < j1; j += kThreads) {
             dst[doff + (int64_t) di * ds] = src[soff + (int64_t) si * ss];
             si += sstep;
