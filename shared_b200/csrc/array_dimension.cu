@@ -237,8 +237,7 @@ __global__ void __launch_bounds__(kThreads) reduce_lines_thread_kernel(const dou
     const double mu = SQ ? mean[ooff] : 0.0;
     double acc = rr_identity<OP>();
     bool nan = false;
-    for (int64_t j = lo; j < hi; j++) {
-        double x = in[ioff + j * L.ilstride];
+    auto take = [&](double x) {
         if (SQ) {
             x = (x - mu) * (x - mu);
         }
@@ -248,6 +247,21 @@ __global__ void __launch_bounds__(kThreads) reduce_lines_thread_kernel(const dou
         } else {
             acc = rr_combine<OP>(acc, x);
         }
+    };
+    int64_t j = lo;
+    for (; j + 7 < hi; j += 8) {  // eight loads in flight, folded in the reference's order
+        double x[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            x[e] = in[ioff + (j + e) * L.ilstride];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            take(x[e]);
+        }
+    }
+    for (; j < hi; j++) {
+        take(in[ioff + j * L.ilstride]);
     }
     if ((OP == RR_MAX || OP == RR_MIN) && nan) {
         acc = __longlong_as_double(0x7ff8000000000000LL);
