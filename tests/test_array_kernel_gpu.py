@@ -179,12 +179,16 @@ def test_rrop_max_min_nan_and_zero_semantics(k):
     """Math.max / Math.min (DimensionOps.java:96-123): a NaN anywhere along the line gives NaN; the folds start from
     -/+Double.MAX_VALUE, so a line of -infinity reduces to -MAX_VALUE under MAX."""
     rng = np.random.default_rng(22)
-    for dims in ([6, 300], [300, 6], [5000, 70], [3, 4096]):
+    for dims in ([6, 300], [300, 6], [5000, 70], [6, 4096]):
         n = int(np.prod(dims))
         src = rng.uniform(-1, 1, n)
         m = src.reshape(dims)
         m[1, 3] = np.nan
         m[2, :] = -np.inf
+        m[3, :] = -0.0           # signed zeros: Math.max(-0.0, +0.0) = +0.0, Math.min = -0.0 (compared bit for bit below)
+        m[3, 5] = 0.0
+        m[4, :] = 0.0
+        m[4, 1] = -0.0
         for dim in (0, 1):
             ddims = [1 if i == dim else dims[i] for i in range(2)]
             for op, red, start in (("RR_MAX", np.max, -np.finfo(np.float64).max), ("RR_MIN", np.min, np.finfo(np.float64).max)):
@@ -192,6 +196,9 @@ def test_rrop_max_min_nan_and_zero_semantics(k):
                 k.rrOp(OP[op], src.copy(), dims, strides(dims), dst, ddims, strides(ddims), dim)
                 want = red(np.concatenate([m, np.full(ddims, start)], axis=dim), axis=dim).ravel()
                 assert np.array_equal(dst, want, equal_nan=True), (dims, dim, op)
+                if dim == 1:  # rows 3 and 4 reduce over both zeros
+                    zero = 0.0 if op == "RR_MAX" else -0.0
+                    assert np.signbit(dst[3]) == np.signbit(zero) and np.signbit(dst[4]) == np.signbit(zero), (dims, op)
 
 
 def test_riop_many_lines_edge_cases(k):
