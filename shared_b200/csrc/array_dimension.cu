@@ -125,10 +125,13 @@ __device__ __forceinline__ double rr_combine(double a, double b) {
 template <int OP, int SQ>
 __device__ __forceinline__ double fold_line(const double *__restrict__ in, int64_t ioff, int64_t lstride, int64_t len,
         int start, int step, double mu) {
-    double acc[8];
+    // sums / products: 8 accumulators; MAX / MIN: 8 loads in flight but 2 accumulators (their fold is ~8 instructions
+    // per point and 8 live accumulators cost the occupancy that hides the loads)
+    constexpr int A = (OP == RR_MAX || OP == RR_MIN) ? 2 : 8;
+    double acc[A];
     bool nan = false;
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
+    for (int e = 0; e < A; e++) {
         acc[e] = rr_identity<OP>();
     }
     int64_t j = start;
@@ -147,9 +150,9 @@ __device__ __forceinline__ double fold_line(const double *__restrict__ in, int64
                 // Math.max / Math.min return NaN if either operand is NaN: fold with the NaN-ignoring fmax / fmin and
                 // remember whether a NaN went by (one compare per point instead of java_max's three selects)
                 nan |= x[e] != x[e];
-                acc[e] = OP == RR_MAX ? fmax(acc[e], x[e]) : fmin(acc[e], x[e]);
+                acc[e % A] = OP == RR_MAX ? fmax(acc[e % A], x[e]) : fmin(acc[e % A], x[e]);
             } else {
-                acc[e] = rr_combine<OP>(acc[e], x[e]);
+                acc[e % A] = rr_combine<OP>(acc[e % A], x[e]);
             }
         }
     }
@@ -161,7 +164,7 @@ __device__ __forceinline__ double fold_line(const double *__restrict__ in, int64
         acc[0] = rr_combine<OP>(acc[0], x);
     }
 #pragma unroll
-    for (int w = 4; w > 0; w >>= 1) {
+    for (int w = A / 2; w > 0; w >>= 1) {
 #pragma unroll
         for (int e = 0; e < w; e++) {
             acc[e] = rr_combine<OP>(acc[e], acc[e + w]);
