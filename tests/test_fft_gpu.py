@@ -211,6 +211,39 @@ def test_3d_device_properties(dims):
     torch.cuda.synchronize()
 
 
+def test_1024_cube_single_gpu():
+    """BASELINE configs[4]'s size on ONE GPU (2^30 points, 16 GiB per array: more than a Java array can hold, so it is
+    reachable through the device tier only): round trip, Parseval, the DC bin and an impulse -- 64-bit indexing."""
+    import torch
+    import shared_b200 as s
+    free, _ = torch.cuda.mem_get_info()
+    if free < 56 * (1 << 30):
+        pytest.skip("needs 3 x 16 GiB of device memory")
+    dims = [1024, 1024, 1024]
+    n = 1 << 30
+    tol = rel_tol(n)
+    x = torch.empty(n, 2, dtype=torch.float64, device="cuda")
+    x.uniform_(-0.5, 0.5, generator=torch.Generator(device="cuda").manual_seed(7))
+    y, z = torch.empty_like(x), torch.empty_like(x)
+    st = torch.cuda.current_stream().cuda_stream
+    fwd, bwd = _dev_plan(s.FORWARD, dims), _dev_plan(s.BACKWARD, dims)
+    fwd.execute(x.data_ptr(), y.data_ptr(), st)
+    ex = sum((x[i:i + (1 << 27)] ** 2).sum().item() for i in range(0, n, 1 << 27))
+    ey = sum((y[i:i + (1 << 27)] ** 2).sum().item() for i in range(0, n, 1 << 27))
+    assert abs(ey / (n * ex) - 1.0) < 1e-12
+    assert abs(y[0, 0].item() - x[:, 0].sum().item()) < 1e-9 * n ** 0.5
+    bwd.execute(y.data_ptr(), z.data_ptr(), st)
+    z.sub_(x)
+    err = sum((z[i:i + (1 << 27)] ** 2).sum().item() for i in range(0, n, 1 << 27)) ** 0.5 / ex ** 0.5
+    assert err < tol, err
+    x.zero_()
+    x[(1 << 30) - 12345, 0] = 1.0     # an impulse far beyond 2^31 bytes
+    fwd.execute(x.data_ptr(), y.data_ptr(), st)
+    worst = max(((y[i:i + (1 << 27)] ** 2).sum(dim=1) - 1.0).abs().max().item() for i in range(0, n, 1 << 27))
+    assert worst < 1e-12
+    torch.cuda.synchronize()
+
+
 def test_3d_against_oracle_64(svc):
     # the largest 3-D cube the CPU oracle finishes in about a second
     dims = [64, 64, 64]
