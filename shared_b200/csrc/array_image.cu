@@ -52,6 +52,80 @@ __global__ void __launch_bounds__(kThreads) histogram_scatter_kernel(const doubl
     }
 }
 
+// First scan of the integral image fused with the copy: the running sum along dimension 0 of "dst with the source
+// block placed at +1", without materialising that array first. A CTA owns a strip of 32 adjacent destination lines
+// (lane = line) and walks down them in blocks of 8 warps x kImgRows rows, like the rdOp strip scan
+// (array_dimension.cu). Row 0 of a line is the destination's own border value; rows >= 1 come from the source when
+// the line is an interior one (every other coordinate >= 1) and from the destination otherwise -- so whatever the
+// border holds takes part exactly as in the reference (NativeImageKernel.cpp:96-118).
+constexpr int kImgRows = 32;
+
+struct ImgLines {
+    int nd;                      // the other dimensions (destination sizes), fastest destination stride first
+    int64_t size[kMaxDims], dstride[kMaxDims], sstride[kMaxDims];
+    int64_t n_lines, len;        // len = destination size along dimension 0
+    int64_t dlstride, slstride;  // strides along dimension 0
+};
+
+__global__ void __launch_bounds__(kThreads) integral_first_scan_kernel(const double *__restrict__ src, double *dst,
+        ImgLines L) {
+    constexpr int NW = kThreads / 32;
+    __shared__ double tot[2][NW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t strips = (L.n_lines + 31) / 32;
+    for (int64_t sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
+        int64_t m = sidx * 32 + lane;
+        const bool live = m < L.n_lines;
+        int64_t doff = 0, soff = 0;
+        bool interior = live;
+        if (live) {
+            for (int k = 0; k < L.nd; k++) {
+                const int64_t q = m / L.size[k];
+                const int64_t r = m - q * L.size[k];
+                doff += r * L.dstride[k];
+                soff += (r - 1) * L.sstride[k];
+                interior = interior && r >= 1;
+                m = q;
+            }
+        }
+        double carry = 0.0;
+        int buf = 0;
+        for (int64_t base = 0; base < L.len; base += (int64_t) NW * kImgRows, buf ^= 1) {
+            const int64_t r0 = base + (int64_t) warp * kImgRows;
+            double x[kImgRows];
+#pragma unroll
+            for (int e = 0; e < kImgRows; e++) {
+                const int64_t r = r0 + e;
+                double v = 0.0;
+                if (live && r < L.len) {
+                    v = (interior && r >= 1) ? src[soff + (r - 1) * L.slstride] : dst[doff + r * L.dlstride];
+                }
+                x[e] = v;
+            }
+#pragma unroll
+            for (int e = 1; e < kImgRows; e++) {
+                x[e] = x[e - 1] + x[e];
+            }
+            tot[buf][warp][lane] = x[kImgRows - 1];
+            __syncthreads();
+            double pre = carry;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const double t = tot[buf][w][lane];
+                pre = w < warp ? pre + t : pre;
+                carry = carry + t;
+            }
+#pragma unroll
+            for (int e = 0; e < kImgRows; e++) {
+                if (live && r0 + e < L.len) {
+                    dst[doff + (r0 + e) * L.dlstride] = pre + x[e];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 static void rethrow_rc(int rc) {
     if (rc != 0) {
         throw std::runtime_error(std::string(sstc_last_error()));
@@ -97,6 +171,45 @@ int sstc_integral_image_dev(const double *src, int64_t nsrc, const int32_t *sD, 
             }
         }
         if (nsrc == 0) {
+            return;
+        }
+        // Fused path: dimension 0 is not the fastest one and there are enough lines for coalesced strips -- the copy
+        // is folded into the first scan (8 B read + 8 B written per point instead of 32), the other dimensions are
+        // scanned in place afterwards.
+        int fastest = 0;
+        int64_t n_lines = 1;
+        for (int d = 1; d < nd; d++) {
+            n_lines *= dD[d];
+            if (dS[d] < dS[fastest]) {
+                fastest = d;
+            }
+        }
+        if (nd >= 2 && fastest != 0 && n_lines >= 1024 && dD[0] >= 2) {
+            ImgLines L;
+            L.nd = 0;
+            L.n_lines = n_lines;
+            L.len = dD[0];
+            L.dlstride = dS[0];
+            L.slstride = sS[0];
+            std::vector<int> order;
+            for (int d = 1; d < nd; d++) {
+                order.push_back(d);
+            }
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dS[a] < dS[b]; });
+            for (int d : order) {
+                L.size[L.nd] = dD[d];
+                L.dstride[L.nd] = dS[d];
+                L.sstride[L.nd] = sS[d];
+                L.nd++;
+            }
+            const int grid = (int) std::min<int64_t>((n_lines + 31) / 32, (int64_t) sm_count() * 8);
+            integral_first_scan_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(src, dst, L);
+            check_launch("integral_first_scan_kernel");
+            std::vector<int32_t> op;
+            for (int d = 1; d < nd; d++) {
+                op.push_back(d);
+            }
+            rethrow_rc(sstc_rdop_dev(RD_SUM, dst, ndst, dD, dS, nd, dst, ndst, op.data(), (int) op.size(), stream));
             return;
         }
         // the source block lands at (1, 1, ...): map bounds are (srcStart, dstStart, size) per dimension

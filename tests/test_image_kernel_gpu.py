@@ -33,7 +33,9 @@ def test_replay_reference_tests(k):
 
 CASES = [([1], "FAR"), ([7], "FAR"), ([300], "FAR"), ([5, 9], "FAR"), ([5, 9], "NEAR"), ([64, 33], "FAR"),
          ([257, 300], "NEAR"), ([3, 4, 5], "FAR"), ([3, 4, 5], "NEAR"), ([20, 31, 17], "FAR"), ([2, 3, 2, 4], "NEAR"),
-         ([1, 6], "FAR"), ([6, 1], "NEAR")]
+         ([1, 6], "FAR"), ([6, 1], "NEAR"),
+         # enough lines off dimension 0 for the fused copy + first scan
+         ([70, 1500], "FAR"), ([40, 30, 50], "FAR"), ([300, 40, 33], "FAR"), ([3, 2000], "FAR"), ([1500, 70], "NEAR")]
 
 
 @needs_ref
