@@ -53,3 +53,35 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".java")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle|oracle/|libsst_oracle|libsst_ref", src, re.M), f
+
+
+def test_jni_glue_covers_every_java_native():
+    """Every `native` method of the Java providers has its JNI export in jni_glue.cpp, and every export has a native
+    method (the glue cannot be linked here -- no JDK -- so this is what keeps the two sides from drifting apart)."""
+    java_dir = os.path.join(ROOT, "shared_b200", "java", "org", "sharedx", "cuda")
+    glue = open(os.path.join(ROOT, "shared_b200", "csrc", "jni", "jni_glue.cpp")).read()
+    glue = glue.replace("AK(", "Java_org_sharedx_cuda_CudaArrayKernel_(")
+    exported = set(re.findall(r"Java_org_sharedx_cuda_(\w+?)_\(?(\w+)\)?\s*\(JNIEnv", glue))
+    declared = set()
+    for f in os.listdir(java_dir):
+        src = re.sub(r"/\*.*?\*/", "", open(os.path.join(java_dir, f)).read(), flags=re.S)
+        cls = f[:-5]
+        for m in re.finditer(r"\bnative\b[^;(]*?(\w+)\s*\(", src):
+            declared.add((cls, m.group(1)))
+    assert len(declared) >= 20
+    assert declared == exported, (sorted(declared - exported), sorted(exported - declared))
+
+
+def test_python_mirrors_have_the_reference_method_names():
+    """The host-side mirrors expose the SPI method names of the reference interfaces (ArrayKernel.java:285-674,
+    FftService.java:50-105, ImageKernel.java:56-80) -- the parity tests read like the reference's own."""
+    from shared_b200.array_kernel import CudaArrayKernel
+    from shared_b200.fft_service import CudaFftService
+    from shared_b200.image_kernel import CudaImageKernel
+    for name in ("randomize derandomize map slice rrOp riOp rdOp raOp caOp ruOp cuOp iuOp eOp convert mul diag svd eigs "
+                 "invert find insertSparse sliceSparse").split():
+        assert callable(getattr(CudaArrayKernel, name)), name
+    for name in "fft ifft rfft rifft setHint getHint".split():
+        assert callable(getattr(CudaFftService, name)), name
+    for name in "createIntegralImage createIntegralHistogram".split():
+        assert callable(getattr(CudaImageKernel, name)), name
