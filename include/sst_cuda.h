@@ -129,6 +129,16 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
         int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
         void *stream);
 
+/* The mirrored line scatter, for the inverse slab transform. The input is (nblocks, block_planes, plane_lines, len):
+ * block q holds the planes that belong to rank q. The call transforms every line of planes [first, first + group) of
+ * every block and stores line yl of plane xl of block q at d_out_blocks[q] + (xl*dst_plane_lines + yl)*len, i.e.
+ * into a destination whose planes have dst_plane_lines lines (d_out_blocks[q] already points at this rank's first
+ * line inside a plane). Issued plane group by plane group so that the receiver can start its last axis on a group
+ * while later groups are in flight. */
+int sstc_fft_planes_scatter_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int32_t block_planes,
+        int32_t plane_lines, int32_t dst_plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale,
+        int64_t max_ctas, void *stream);
+
 /* Cross-GPU barrier kernel (one process per GPU): d_flag_arrays[r] is rank r's array of 8 uint64 epoch slots,
  * mapped by every rank (sstc_ipc_*) and zero-initialised (at least 9 slots: slot 8 is the rank's own call
  * counter); `epoch` must increase with every call, or be 0 to let the kernel count calls itself (for use inside

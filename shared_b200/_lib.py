@@ -55,6 +55,9 @@ SIGNATURES = {
     "sstc_fft_lines_scatter_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int64,
                                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
+    "sstc_fft_planes_scatter_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
     "sstc_peer_barrier_dev": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]),
     "sstc_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "sstc_ipc_open": (ctypes.c_int, [ctypes.c_char_p, c_void_pp]),

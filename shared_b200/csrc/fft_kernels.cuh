@@ -59,7 +59,11 @@ struct FftPassArgs {
     // [ls_first, ls_first + ls_group) of every block of every plane and stores line yl of block q of plane xl
     // at blk[q] + (xl*ls_block_lines + yl)*L -- whole 16*L-byte lines per destination, which is what lets
     // the exchange pass of the slab transform run in groups that the next pass can start consuming.
-    int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines;
+    // ls_sub > 0 selects the mirrored form used by the inverse slab transform: the input is (nblk, ls_block_lines
+    // planes, ls_sub lines, L); this launch transforms every line of planes [ls_first, ls_first + ls_group) of every
+    // block and stores line yl of plane xl of block q at blk[q] + (xl*ls_plane_lines + yl)*L (ls_plane_lines = the
+    // destination's lines per plane).
+    int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines, ls_sub;
     // Fused convolution (EXT kernels and the any-length kernel; all off when mul == nullptr and crop_cols == 0):
     //   mul        every point loaded by a c2c (natural layout) or c2r pass is first multiplied by mul[same index]
     //              -- the eMul of ConvolutionCache.convolve folded into the first inverse pass;
@@ -277,12 +281,20 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
         if (EXT && a.ls_group > 0) {
             // line scatter: this launch covers, for every plane xl and every destination block q, the lines
             // [ls_first, ls_first + ls_group) of that block; a whole line goes to one destination.
-            const int64_t yq = line % a.ls_group, t1 = line / a.ls_group;
-            const int q = (int) (t1 % a.ls_nblk);
-            const int64_t xl = t1 / a.ls_nblk;
-            const int64_t yl = a.ls_first + yq;
-            in_base = (xl * a.ls_plane_lines + (int64_t) q * a.ls_block_lines + yl) * L;
-            out_line = a.blk[q] + (xl * a.ls_block_lines + yl) * L;
+            if (a.ls_sub > 0) {
+                const int64_t yl = line % a.ls_sub, t1 = line / a.ls_sub;
+                const int q = (int) (t1 % a.ls_nblk);
+                const int64_t xl = a.ls_first + t1 / a.ls_nblk;
+                in_base = (((int64_t) q * a.ls_block_lines + xl) * a.ls_sub + yl) * L;
+                out_line = a.blk[q] + (xl * a.ls_plane_lines + yl) * L;
+            } else {
+                const int64_t yq = line % a.ls_group, t1 = line / a.ls_group;
+                const int q = (int) (t1 % a.ls_nblk);
+                const int64_t xl = t1 / a.ls_nblk;
+                const int64_t yl = a.ls_first + yq;
+                in_base = (xl * a.ls_plane_lines + (int64_t) q * a.ls_block_lines + yl) * L;
+                out_line = a.blk[q] + (xl * a.ls_block_lines + yl) * L;
+            }
         }
     }
 

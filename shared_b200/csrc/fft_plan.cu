@@ -352,7 +352,7 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.mode = mode;
     a.inverse = inverse;
     a.ksplit = a.in_ksplit = 0;
-    a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = 0;
+    a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = a.ls_sub = 0;
     a.ntiles = a.grid_limit = 0;
     a.reverse = reverse;
     a.mul = fuse ? fuse->mul : nullptr;
@@ -969,6 +969,43 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
         a.ls_first = first;
         a.ls_block_lines = plane_lines / nblocks;
         a.ls_plane_lines = plane_lines;
+        a.grid_limit = max_ctas > 0 ? max_ctas : 0;
+        dispatch_axis(a, len, false, as_stream(stream));
+    });
+}
+
+int sstc_fft_planes_scatter_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int32_t block_planes,
+        int32_t plane_lines, int32_t dst_plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale,
+        int64_t max_ctas, void *stream) {
+    return guarded([&] {
+        if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || block_planes <= 0 || plane_lines <= 0 ||
+                dst_plane_lines < plane_lines || len <= 0 || first < 0 || group <= 0 || first + group > block_planes) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (!(len >= 8 && len <= 4096 && (len & (len - 1)) == 0)) {
+            throw std::runtime_error("line scatter needs a power-of-two length between 8 and 4096");
+        }
+        FftPassArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = reinterpret_cast<const double2 *>(d_in);
+        a.tw = pow2_twiddles_for(len);
+        a.outer = (int64_t) nblocks * group * plane_lines;  // lines in this launch
+        a.inner = 1;
+        a.in_plane = a.out_plane = len;
+        a.in_kstride = a.out_kstride = 1;
+        a.scale = scale;
+        a.mode = MODE_C2C;
+        a.inverse = inverse ? 1 : 0;
+        a.blk_pitch = a.in_blk_pitch = 1;
+        for (int q = 0; q < nblocks; q++) {
+            a.blk[q] = static_cast<double2 *>(d_out_blocks[q]);
+        }
+        a.ls_group = group;
+        a.ls_nblk = nblocks;
+        a.ls_first = first;
+        a.ls_block_lines = block_planes;
+        a.ls_plane_lines = dst_plane_lines;
+        a.ls_sub = plane_lines;
         a.grid_limit = max_ctas > 0 ? max_ctas : 0;
         dispatch_axis(a, len, false, as_stream(stream));
     });

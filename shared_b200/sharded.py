@@ -79,6 +79,14 @@ class CudaEngine:
             int(first), int(group), int(bool(inverse)), float(scale), int(max_ctas),
             ctypes.c_void_p(self._stream())))
 
+    def planes_scatter(self, src, dst_blocks, block_planes, plane_lines, dst_plane_lines, length, first, group,
+                       inverse=False, scale=1.0, max_ctas=0):
+        dp = (ctypes.c_void_p * len(dst_blocks))(*[self._ptr(b) for b in dst_blocks])
+        _lib.check(_lib.lib().sstc_fft_planes_scatter_dev(
+            ctypes.c_void_p(self._ptr(src)), dp, len(dst_blocks), int(block_planes), int(plane_lines),
+            int(dst_plane_lines), int(length), int(first), int(group), int(bool(inverse)), float(scale), int(max_ctas),
+            ctypes.c_void_p(self._stream())))
+
     def peer_barrier(self, flag_ptrs, rank, epoch):
         fp = (ctypes.c_void_p * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
         _lib.check(_lib.lib().sstc_peer_barrier_dev(fp, len(flag_ptrs), int(rank), ctypes.c_uint64(int(epoch)),
@@ -285,8 +293,42 @@ class SlabFft3d:
         e.axis(out, out, 1, self.d0, self.y_loc * self.d2)                                       # x
         return out
 
+    def _inverse_pipe(self, y):
+        """The forward pipeline mirrored: x pass locally (y is preserved), then the z pass is the exchange pass -- it
+        stores whole lines into the owners' natural slabs, plane group by plane group -- and after each group's
+        barrier the y pass (with the 1/N scale) runs on that group's planes beside the rest of the exchange."""
+        e, p = self.engine, self.world
+        dev = e.device
+        cur = torch.cuda.current_stream(dev)
+        buf = self.peer[self._step % 2]
+        self._step += 1
+        e.axis(y, self.work, 1, self.d0, self.y_loc * self.d2, inverse=True)                      # x, local
+        x_done = cur.record_event()
+        base = [buf.ptrs[q] + self.rank * self.y_loc * self.d2 * 16 for q in range(p)]
+        ng = next(g for g in (self.groups, 4, 2, 1) if self.x_loc % g == 0)
+        xg = self.x_loc // ng
+        plane = self.d1 * self.d2
+        with torch.cuda.stream(self.s_z):
+            self.s_z.wait_event(x_done)
+            for g in range(ng):
+                e.planes_scatter(self.work, base, self.x_loc, self.y_loc, self.d1, self.d2, g * xg, xg, inverse=True,
+                                 max_ctas=self.exchange_ctas)                                      # z + transpose
+                sent = self.s_z.record_event()
+                self.s_bar.wait_event(sent)
+                with torch.cuda.stream(self.s_bar):
+                    e.peer_barrier(self.flags.ptrs, self.rank, 0)
+                    arrived = self.s_bar.record_event()
+                self.s_x.wait_event(arrived)
+                with torch.cuda.stream(self.s_x):
+                    ptr = buf.local_ptr + g * xg * plane * 16
+                    e.axis(ptr, ptr, xg, self.d1, self.d2, inverse=True, scale=1.0 / self.n_total)  # y on this group
+        cur.wait_stream(self.s_x)
+        return buf.tensor
+
     def inverse(self, y):
         """y: this rank's transposed slab. Returns this rank's natural slab of ifft (scaled by 1/N)."""
+        if self.exchange == "pipe":
+            return self._inverse_pipe(y)
         e, p = self.engine, self.world
         row = self.d1 * self.d2  # one x row of a natural slab
         if self.exchange in ("p2p", "pipe"):

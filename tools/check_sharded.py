@@ -40,6 +40,22 @@ for dims in ([64, 64, 64], [128, 64, 32], [512, 512, 512]):
         if rank == 0:
             print("dims", dims, "world", world, mode, "fwd rel-L2 vs 1-GPU %.2e" % err, "bit-identical", exact,
                   "roundtrip %.2e" % rt, "OK" if ok else "FAIL", flush=True)
+        if dims[0] >= 512:  # inverse timing (eager launches), max over ranks
+            spec = out.clone()
+            for _ in range(3):
+                slab.inverse(spec)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                slab.inverse(spec)
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / 20], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print("dims", dims, "world", world, mode, "inverse ms %.4f" % t.item(), flush=True)
         torch.cuda.synchronize()
         dist.barrier()
         slab.close()
