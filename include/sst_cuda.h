@@ -244,6 +244,15 @@ int sstc_diag_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, in
 int sstc_invert(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size);
 int sstc_invert_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, int size, void *stream);
 
+/* svd (Bindings.cpp:127-132 -> LinearAlgebraOpsSvd.cpp:26-72): thin SVD of an n_rows x n_cols matrix, n_rows >= n_cols,
+ * given row-major (strides n_cols, 1) or as the transpose of a row-major matrix (strides 1, n_rows). Outputs row-major
+ * U (n_rows x n_cols), S (n_cols, descending), V (n_cols x n_cols) with U diag(S) V^T = A. Computed by one-sided Jacobi
+ * rotations, so U and V agree with the reference's JAMA port up to the sign of each singular-vector pair. */
+int sstc_svd(const double *src, int64_t nsrc, int src_stride_row, int src_stride_col, double *u, int64_t nu, double *sv,
+        int64_t ns, double *v, int64_t nv, int n_rows, int n_cols);
+int sstc_svd_dev(const double *src, int64_t nsrc, int src_stride_row, int src_stride_col, double *u, int64_t nu, double *sv,
+        int64_t ns, double *v, int64_t nv, int n_rows, int n_cols, void *stream);
+
 /* find (Bindings.cpp:160-163 -> IndexOps.cpp:26-130): `logical` holds one index per dimension with exactly one -1
  * marking the active dimension; along that line of the int array (as riOp writes it: positions, then -1 padding)
  * *count = number of non-negative entries, and out[0 .. *count) = the first *count entries of the line. `out` must

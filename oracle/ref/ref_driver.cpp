@@ -176,6 +176,14 @@ int sstref_invert(const double *src, int nsrc, double *dst, int ndst, int size) 
     return env_done(env);
 }
 
+int sstref_svd(const double *src, int nsrc, int rs, int cs, double *u, int nu, double *sv, int ns, double *v, int nv, int nrows,
+        int ncols) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), uu = DARR(u, nu), ss = DARR(sv, ns), vv = DARR(v, nv);
+    LinearAlgebraOps::svd(env, 0, &s, rs, cs, &uu, &ss, &vv, nrows, ncols);
+    return env_done(env);
+}
+
 /* returns the length of the result (copied into out, capacity cap), or -1 on a Java exception */
 int sstref_find(const int *src, int nsrc, const int *sD, const int *sS, int nd, const int *logical, int *out, int cap) {
     JNIEnv *env = env_get();

@@ -131,6 +131,10 @@ class RefKernel:
     def invert(self, srcV, dstV, size):
         self._chk(self._l.sstref_invert(_p(_f64(srcV)), srcV.size, _p(_f64(dstV)), dstV.size, int(size)))
 
+    def svd(self, srcV, srcStrideRow, srcStrideCol, uV, sV, vV, nRows, nCols):
+        self._chk(self._l.sstref_svd(_p(_f64(srcV)), srcV.size, int(srcStrideRow), int(srcStrideCol), _p(_f64(uV)), uV.size,
+                                     _p(_f64(sV)), sV.size, _p(_f64(vV)), vV.size, int(nRows), int(nCols)))
+
     def find(self, srcV, srcD, srcS, logical):
         sD, sS, lg = _i32(srcD), _i32(srcS), _i32(logical)
         assert srcV.dtype == np.int32

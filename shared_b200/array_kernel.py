@@ -6,8 +6,8 @@ NativeArrayKernel (src/org/shared/array/jni/NativeArrayKernel.java:41-154): arra
 int32 arrays standing in for Java double[] / int[], mutated in place where the Java contract mutates them.
 It is the Python twin of shared_b200/java/org/sharedx/cuda/CudaArrayKernel.java; both sit on the host tier of
 include/sst_cuda.h. `DeviceArrayKernel` is the device tier (device pointers + stream) used by bench.py.
-Members outside the north-star families (svd, eigs, invert, find, insertSparse, sliceSparse) raise
-NotImplementedError -- the Java twin throws UnsupportedOperationException; there is no CPU fallback.
+Of the members outside the north-star families, invert, svd and find are provided; eigs, insertSparse and sliceSparse
+raise NotImplementedError -- the Java twin throws UnsupportedOperationException; there is no CPU fallback.
 """
 import ctypes
 import time
@@ -156,6 +156,11 @@ class CudaArrayKernel:
         """ArrayKernel.invert (ArrayKernel.java:576-586; LinearAlgebraOpsLu.cpp:26-76)."""
         _lib.check(self._l.sstc_invert(_vp(srcV), srcV.size, _vp(dstV), dstV.size, int(size)))
 
+    def svd(self, srcV, srcStrideRow, srcStrideCol, uV, sV, vV, nRows, nCols):
+        """ArrayKernel.svd (ArrayKernel.java:558-560; LinearAlgebraOpsSvd.cpp:26-72)."""
+        _lib.check(self._l.sstc_svd(_vp(srcV), srcV.size, int(srcStrideRow), int(srcStrideCol), _vp(uV), uV.size, _vp(sV),
+                                    sV.size, _vp(vV), vV.size, int(nRows), int(nCols)))
+
     def find(self, srcV, srcD, srcS, logical):
         """ArrayKernel.find (ArrayKernel.java:603; IndexOps.java:44-91): returns a new int32 array."""
         if srcV.dtype != np.int32:
@@ -174,7 +179,7 @@ class CudaArrayKernel:
     def _unsupported(self, *args, **kwargs):
         raise NotImplementedError("not provided by the CUDA ArrayKernel (no CPU fallback)")
 
-    svd = eigs = insertSparse = sliceSparse = _unsupported
+    eigs = insertSparse = sliceSparse = _unsupported
 
 
 class DeviceArrayKernel:

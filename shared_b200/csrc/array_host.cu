@@ -3,6 +3,7 @@
 // pinned Java arrays; each call stages them through HBM (H2D, device-tier kernels, D2H of whatever the Java
 // contract says is mutated) on the legacy default stream and returns when the host arrays are up to date.
 // Where the reference pins with JNI_ABORT (inputs, no copy-back) nothing is copied back here either.
+#include <algorithm>
 #include <string>
 
 #include "array_common.cuh"
@@ -281,6 +282,27 @@ int sstc_invert(const double *src, int64_t nsrc, double *dst, int64_t ndst, int 
         rethrow(sstc_invert_dev(static_cast<const double *>(s0.dev), nsrc, static_cast<double *>(d.dev), ndst, size,
                 nullptr));
         d.download();
+        finish();
+    });
+}
+
+int sstc_svd(const double *src, int64_t nsrc, int src_stride_row, int src_stride_col, double *u, int64_t nu, double *sv,
+        int64_t ns, double *v, int64_t nv, int n_rows, int n_cols) {
+    return guarded([&] {
+        if (nsrc < 0 || nu < 0 || ns < 0 || nv < 0 || (nsrc > 0 && !src) || (nu > 0 && !u) || (ns > 0 && !sv) ||
+                (nv > 0 && !v)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        static thread_local Scratch extra;  // a fourth staging buffer: src, U, S, V
+        Staged s0(0, src, nsrc * 8, true), du(1, u, nu * 8, false), dv(2, v, nv * 8, false);
+        double *ds = static_cast<double *>(extra.get(std::max<int64_t>(ns, 1) * 8));
+        rethrow(sstc_svd_dev(static_cast<const double *>(s0.dev), nsrc, src_stride_row, src_stride_col,
+                static_cast<double *>(du.dev), nu, ds, ns, static_cast<double *>(dv.dev), nv, n_rows, n_cols, nullptr));
+        du.download();
+        dv.download();
+        if (ns > 0) {
+            SSTC_CUDA(cudaMemcpyAsync(sv, ds, (size_t) ns * 8, cudaMemcpyDeviceToHost, 0));
+        }
         finish();
     });
 }

@@ -1,4 +1,4 @@
-// array_linalg.cu -- ArrayKernel.invert and ArrayKernel.find.
+// array_linalg.cu -- ArrayKernel.invert, ArrayKernel.svd and ArrayKernel.find.
 //
 // invert replaces native/src/shared/LinearAlgebraOpsLu.cpp:26-176 (JAMA's LU with partial pivoting, then L / U
 // solves against the permuted identity; Java twin: LinearAlgebraOps.java). Same factorisation, same pivot rule
@@ -13,6 +13,7 @@
 // written by riOp: positions, then -1 padding) count the non-negative entries and return that many leading entries.
 #include <math.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -161,6 +162,126 @@ __global__ void __launch_bounds__(256) find_kernel(const int32_t *__restrict__ s
     }
 }
 
+// ---- svd: one-sided Jacobi (Hestenes) ---------------------------------------------------------------------------
+// The reference runs JAMA's Golub-Kahan bidiagonalisation + implicit QR (LinearAlgebraOpsSvd.cpp:26-560), a serial
+// algorithm. Here: rotate column pairs of a column-major working copy W until all columns are orthogonal, the same
+// rotations accumulated into V; then sigma_j = |W_j|, U_j = W_j / sigma_j, sorted by descending sigma like JAMA. The
+// n/2 disjoint pairs of one round of a round-robin schedule are independent: one CTA per pair, n - 1 launches per
+// sweep, sweeps until a whole sweep rotates nothing. U, S, V agree with the reference's up to the sign of each
+// singular-vector pair (and the order within repeated singular values); U S V^T = A either way.
+
+__global__ void __launch_bounds__(256) svd_load_kernel(const double *__restrict__ src, int64_t rs, int64_t cs, double *w,
+        double *v, int m, int n) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x, tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < (int64_t) m * n; i += stride) {
+        const int64_t col = i / m, row = i - col * m;
+        w[i] = src[row * rs + col * cs];
+    }
+    for (int64_t i = tid; i < (int64_t) n * n; i += stride) {
+        v[i] = (i / n == i % n) ? 1.0 : 0.0;
+    }
+}
+
+__device__ __forceinline__ double block_sum_256(double x, double *sh) {
+    for (int off = 16; off > 0; off >>= 1) {
+        x += __shfl_down_sync(0xffffffffu, x, off);
+    }
+    __syncthreads();  // sh may still be read from a previous call
+    if ((threadIdx.x & 31) == 0) {
+        sh[threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) {
+        t += sh[w];
+    }
+    return t;
+}
+
+// Round `r` of the circle schedule over n2 (even) players: pair k is (n2-1, r) for k = 0, else
+// ((r + k) mod (n2-1), (r - k) mod (n2-1)); players >= n are byes.
+__global__ void __launch_bounds__(256) svd_round_kernel(double *w, double *v, int m, int n, int n2, int r, double tol,
+        int *rotations) {
+    __shared__ double sh[8];
+    __shared__ double cs[2];
+    const int k = blockIdx.x;
+    const int a = k == 0 ? n2 - 1 : (r + k) % (n2 - 1), b = k == 0 ? r : (r - k + n2 - 1) % (n2 - 1);
+    const int p = a < b ? a : b, q = a < b ? b : a;
+    if (q >= n) {
+        return;
+    }
+    double *wp = w + (int64_t) p * m, *wq = w + (int64_t) q * m;
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int i = threadIdx.x; i < m; i += 256) {
+        const double x = wp[i], y = wq[i];
+        al += x * x;
+        be += y * y;
+        ga += x * y;
+    }
+    al = block_sum_256(al, sh);
+    be = block_sum_256(be, sh);
+    ga = block_sum_256(ga, sh);
+    if (!(fabs(ga) > tol * sqrt(al * be)) || ga == 0.0) {
+        return;  // uniform: every thread holds the same sums
+    }
+    if (threadIdx.x == 0) {
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = zeta == 0.0 ? 1.0 : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        cs[0] = c;
+        cs[1] = c * t;
+        atomicAdd(rotations, 1);
+    }
+    __syncthreads();
+    const double c = cs[0], sn = cs[1];
+    for (int i = threadIdx.x; i < m; i += 256) {
+        const double x = wp[i], y = wq[i];
+        wp[i] = c * x - sn * y;
+        wq[i] = sn * x + c * y;
+    }
+    double *vp = v + (int64_t) p * n, *vq = v + (int64_t) q * n;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double x = vp[i], y = vq[i];
+        vp[i] = c * x - sn * y;
+        vq[i] = sn * x + c * y;
+    }
+}
+
+__global__ void __launch_bounds__(256) svd_norm_kernel(const double *__restrict__ w, double *sigma, int m) {
+    __shared__ double sh[8];
+    const double *col = w + (int64_t) blockIdx.x * m;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < m; i += 256) {
+        acc += col[i] * col[i];
+    }
+    acc = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) {
+        sigma[blockIdx.x] = sqrt(acc);
+    }
+}
+
+// Row-major outputs in sorted order: U (m x n), S (n), V (n x n).
+__global__ void __launch_bounds__(256) svd_store_kernel(const double *__restrict__ w, const double *__restrict__ v,
+        const double *__restrict__ sigma, const int32_t *__restrict__ perm, double *u_out, double *s_out, double *v_out,
+        int m, int n) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x, tid = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = tid; i < (int64_t) m * n; i += stride) {
+        const int64_t row = i / n, jj = i - row * n;
+        const int j = perm[jj];
+        const double sg = sigma[j];
+        u_out[i] = sg > 0.0 ? w[(int64_t) j * m + row] / sg : 0.0;
+    }
+    for (int64_t i = tid; i < (int64_t) n * n; i += stride) {
+        const int64_t row = i / n, jj = i - row * n;
+        v_out[i] = v[(int64_t) perm[jj] * n + row];
+    }
+    for (int64_t i = tid; i < n; i += stride) {
+        s_out[i] = sigma[perm[i]];
+    }
+}
+
+static thread_local Scratch t_svd_w, t_svd_v, t_svd_s, t_svd_perm;
+
 static thread_local Scratch t_lu, t_piv, t_small;
 
 }  // namespace sstc
@@ -220,6 +341,60 @@ int sstc_invert_dev(const double *src, int64_t nsrc, double *dst, int64_t ndst, 
         }
         check_launch("lu solve kernels");
         count_launch(3 * n);
+    });
+}
+
+int sstc_svd_dev(const double *src, int64_t nsrc, int src_stride_row, int src_stride_col, double *u, int64_t nu, double *sv,
+        int64_t ns, double *v, int64_t nv, int n_rows, int n_cols, void *stream) {
+    return guarded([&] {
+        cudaStream_t s = as_stream(stream);
+        const int m = n_rows, n = n_cols;
+        // LinearAlgebraOpsSvd.cpp:42-50: tall or square, row-major or its transpose
+        if (m < 0 || n < 0 || m < n || nsrc != (int64_t) m * n || nu != (int64_t) m * n || ns != n || nv != (int64_t) n * n ||
+                !((src_stride_row == n && src_stride_col == 1) || (src_stride_row == 1 && src_stride_col == m)) ||
+                (nsrc > 0 && (!src || !u)) || (n > 0 && (!sv || !v))) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (n == 0) {
+            return;
+        }
+        double *w = static_cast<double *>(t_svd_w.get((int64_t) m * n * 8));
+        double *vv = static_cast<double *>(t_svd_v.get((int64_t) n * n * 8));
+        double *sigma = static_cast<double *>(t_svd_s.get((int64_t) n * 8));
+        int32_t *perm = static_cast<int32_t *>(t_svd_perm.get((int64_t) n * 4));
+        int *rot = static_cast<int *>(t_small.get(sizeof(int)));
+        const int grid = stream_grid((int64_t) m * n);
+        svd_load_kernel<<<grid, 256, 0, s>>>(src, src_stride_row, src_stride_col, w, vv, m, n);
+        check_launch("svd_load_kernel");
+        const int n2 = n + (n & 1);
+        for (int sweep = 0; sweep < 60 && n > 1; sweep++) {
+            SSTC_CUDA(cudaMemsetAsync(rot, 0, sizeof(int), s));
+            for (int r = 0; r < n2 - 1; r++) {
+                svd_round_kernel<<<n2 / 2, 256, 0, s>>>(w, vv, m, n, n2, r, 1e-15, rot);
+            }
+            check_launch("svd_round_kernel");
+            count_launch(n2 - 2);
+            int rotated = 0;
+            SSTC_CUDA(cudaMemcpyAsync(&rotated, rot, sizeof(int), cudaMemcpyDeviceToHost, s));
+            SSTC_CUDA(cudaStreamSynchronize(s));
+            if (rotated == 0) {
+                break;
+            }
+        }
+        svd_norm_kernel<<<n, 256, 0, s>>>(w, sigma, m);
+        check_launch("svd_norm_kernel");
+        std::vector<double> hs((size_t) n);
+        SSTC_CUDA(cudaMemcpyAsync(hs.data(), sigma, (size_t) n * 8, cudaMemcpyDeviceToHost, s));
+        SSTC_CUDA(cudaStreamSynchronize(s));
+        std::vector<int32_t> hp((size_t) n);
+        for (int i = 0; i < n; i++) {
+            hp[(size_t) i] = i;
+        }
+        std::stable_sort(hp.begin(), hp.end(), [&](int32_t a, int32_t b) { return hs[(size_t) a] > hs[(size_t) b]; });
+        SSTC_CUDA(cudaMemcpyAsync(perm, hp.data(), (size_t) n * 4, cudaMemcpyHostToDevice, s));
+        svd_store_kernel<<<grid, 256, 0, s>>>(w, vv, sigma, perm, u, sv, v, m, n);
+        check_launch("svd_store_kernel");
+        SSTC_CUDA(cudaStreamSynchronize(s));  // hp goes out of scope
     });
 }
 

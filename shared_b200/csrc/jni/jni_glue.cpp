@@ -524,6 +524,21 @@ JNIEXPORT void JNICALL AK(invert)(JNIEnv *env, jobject, jdoubleArray srcV, jdoub
     raise_last(env, rc);
 }
 
+JNIEXPORT void JNICALL AK(svd)(JNIEnv *env, jobject, jdoubleArray srcV, jint srcStrideRow, jint srcStrideCol,
+        jdoubleArray uV, jdoubleArray sV, jdoubleArray vV, jint nRows, jint nCols) {
+    if (!srcV || !uV || !sV || !vV) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize ns = len(env, srcV), nu = len(env, uV), nsv = len(env, sV), nv = len(env, vV);
+    int rc;
+    {
+        Pin s(env, srcV, true), u(env, uV, false), sv(env, sV, false), v(env, vV, false);
+        rc = sstc_svd(s.as<double>(), ns, srcStrideRow, srcStrideCol, u.as<double>(), nu, sv.as<double>(), nsv,
+                v.as<double>(), nv, nRows, nCols);
+    }
+    raise_last(env, rc);
+}
+
 JNIEXPORT jintArray JNICALL AK(find)(JNIEnv *env, jobject, jintArray srcV, jintArray srcD, jintArray srcS,
         jintArray logical) {
     if (!srcV || !srcD || !srcS || !logical) {

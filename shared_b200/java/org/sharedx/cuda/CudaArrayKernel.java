@@ -10,7 +10,7 @@
  *
  * The sixteen operations on the FFT / array-kernel hot path are native (JNI glue:
  * shared_b200/csrc/jni/jni_glue.cpp, one export per method, same signatures as NativeArrayKernel.java:56-154).
- * Of the interface members outside that path, invert and find are provided; svd, eigs, insertSparse and
+ * Of the interface members outside that path, invert, svd and find are provided; eigs, insertSparse and
  * sliceSparse throw {@link UnsupportedOperationException}: this provider has no CPU fallback.
  */
 package org.sharedx.cuda;
@@ -92,11 +92,10 @@ public class CudaArrayKernel implements ArrayKernel {
 
     //
 
+    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_svd -> sstc_svd (one-sided Jacobi on the GPU). */
     @Override
-    public void svd(double[] srcV, int srcStrideRow, int srcStrideCol, //
-            double[] uV, double[] sV, double[] vV, int nRows, int nCols) {
-        throw new UnsupportedOperationException("svd is not provided by the CUDA ArrayKernel");
-    }
+    final public native void svd(double[] srcV, int srcStrideRow, int srcStrideCol, //
+            double[] uV, double[] sV, double[] vV, int nRows, int nCols);
 
     @Override
     public void eigs(double[] srcV, double[] vecV, double[] valV, int size) {

@@ -428,6 +428,43 @@ def test_invert_matches_reference(k):
 
 
 @needs_ref
+def test_svd_matches_reference(k):
+    """MatrixTest.java:186-203's criterion (|A - U S V^T| summed < 1e-8 over the divisor shapes of 120), singular values
+    against the reference's JAMA port, orthonormal factors, and the singular vectors up to the sign of each pair."""
+    rng = np.random.default_rng(33)
+    shapes = [(120 // i, i) for i in range(1, 121) if 120 % i == 0 and 120 // i >= i] + [(128, 128), (300, 7), (9, 9)]
+    for m, n in shapes:
+        a = rng.uniform(0, 1, (m, n))
+        for transposed in (False, True):
+            if transposed:   # the same matrix handed over as the transpose of a row-major n x m array
+                src, rs, cs = np.ascontiguousarray(a.T).ravel(), 1, m
+            else:
+                src, rs, cs = a.ravel().copy(), n, 1
+            u, sv, v = np.zeros(m * n), np.zeros(n), np.zeros(n * n)
+            ru, rsv, rv = np.zeros(m * n), np.zeros(n), np.zeros(n * n)
+            k.svd(src, rs, cs, u, sv, v, m, n)
+            ref.svd(src.copy(), rs, cs, ru, rsv, rv, m, n)
+            U, V, RU, RV = u.reshape(m, n), v.reshape(n, n), ru.reshape(m, n), rv.reshape(n, n)
+            assert np.abs(a - U @ np.diag(sv) @ V.T).sum() < 1e-8, (m, n, transposed)
+            assert np.all(np.diff(sv) <= 0) and np.max(np.abs(sv - rsv)) < 1e-11 * max(1.0, rsv[0]), (m, n)
+            assert np.max(np.abs(U.T @ U - np.eye(n))) < 1e-12 and np.max(np.abs(V.T @ V - np.eye(n))) < 1e-12
+            gaps = np.abs(np.diff(np.concatenate([rsv, [0.0]])))
+            for j in range(n):  # well-separated singular values: vectors agree up to a common sign
+                if gaps[j] > 1e-2 * rsv[0] and (j == 0 or gaps[j - 1] > 1e-2 * rsv[0]):
+                    sign = np.sign(U[:, j] @ RU[:, j])
+                    assert np.max(np.abs(sign * U[:, j] - RU[:, j])) < 1e-8 and np.max(np.abs(sign * V[:, j] - RV[:, j])) < 1e-8
+    import shared_b200 as s
+    with pytest.raises(s.SstCudaError, match="Invalid arguments"):
+        k.svd(np.zeros(6), 3, 1, np.zeros(6), np.zeros(3), np.zeros(9), 2, 3)      # wide matrices are refused
+    with pytest.raises(s.SstCudaError, match="Invalid arguments"):
+        k.svd(np.zeros(6), 2, 2, np.zeros(6), np.zeros(2), np.zeros(4), 3, 2)      # neither layout
+    z = np.zeros(6)
+    u, sv, v = np.ones(6), np.ones(2), np.ones(4)
+    k.svd(z, 2, 1, u, sv, v, 3, 2)                                                 # the zero matrix: S = 0, A = U S V^T
+    assert np.all(sv == 0) and np.all(np.isfinite(u)) and np.allclose(v.reshape(2, 2).T @ v.reshape(2, 2), np.eye(2))
+
+
+@needs_ref
 def test_find_matches_reference(k):
     rng = np.random.default_rng(32)
     for dims, order in (([7], "FAR"), ([5, 9], "FAR"), ([5, 9], "NEAR"), ([3, 4, 300], "FAR"), ([3, 4, 5], "NEAR")):
@@ -476,7 +513,7 @@ def test_error_messages(k):
     with pytest.raises(E, match="Invalid array types"):  # ObjectArrayTest.java:289-305
         k.map([0, 0, 1], np.zeros(1), [1], [1], np.zeros(1, dtype=np.int32), [1], [1])
     with pytest.raises(NotImplementedError):
-        k.svd()
+        k.eigs()
 
 
 def test_rng_ops_statistics(k):

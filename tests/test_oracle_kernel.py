@@ -63,6 +63,12 @@ def test_invert_and_find_reference_properties():
     assert np.abs(a @ inv.reshape(n, n) - np.eye(n)).sum() < 1e-8
     with pytest.raises(oracle.refkernel.RefKernelError, match="Matrix is singular"):
         ref.invert(np.zeros(9), np.zeros(9), 3)
+    # MatrixTest.java:186-203: A == U S V^T (sum |.| < 1e-8), singular values = numpy's
+    a = rng.uniform(0, 1, (40, 30))
+    u, sv, v = np.zeros(1200), np.zeros(30), np.zeros(900)
+    ref.svd(a.ravel().copy(), 30, 1, u, sv, v, 40, 30)
+    assert np.abs(a - u.reshape(40, 30) @ np.diag(sv) @ v.reshape(30, 30).T).sum() < 1e-8
+    assert np.max(np.abs(sv - np.linalg.svd(a, compute_uv=False))) < 1e-12
     # IndexOps.java:44-91 on a riOp-shaped array: positions, then -1 padding
     v = np.array([3, 1, -1, -1, 0, 2, 5, -1], dtype=np.int32)
     assert list(ref.find(v, [2, 4], [4, 1], [1, -1])) == [0, 2, 5]
