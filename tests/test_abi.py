@@ -89,8 +89,7 @@ def test_python_mirrors_have_the_reference_method_names():
 
 def test_tools_and_entry_points_compile():
     """bench.py, __graft_entry__.py and every driver under tools/ at least byte-compile (they only run on the GPU box)."""
-    import py_compile
     paths = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
     paths += [os.path.join(ROOT, "tools", f) for f in sorted(os.listdir(os.path.join(ROOT, "tools"))) if f.endswith(".py")]
     for p in paths:
-        py_compile.compile(p, doraise=True, cfile=os.devnull)
+        compile(open(p).read(), p, "exec")
