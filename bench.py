@@ -330,6 +330,32 @@ def run_ours(args):
                     "step_model_gbs": 3 * bytes_per_launch / ms_step / 1e6,
                     "step_frac": 3 * bytes_per_launch / ms_step / 1e6 / peak, "passes": passes,
                     "timing": "CUDA events between the launches of back-to-back steps, %d steps" % reps}
+    elif world > 1:
+        # N > 1: the local x pass (fft_pow2_ext_kernel<512, 8, STRIDED> on the received slab) timed alone against the
+        # HBM roofline, and the exchange as NVLink bytes per GPU over the step (the step is exchange-bound from 4 GPUs on)
+        reps = max(5, min(K, 20))
+        out = slab.forward(x)
+        d0, d1, d2 = DIMS
+        cols = (d1 // world) * d2
+
+        def x_pass():
+            slab.engine.axis(out, out, 1, d0, cols)
+
+        x_pass()
+        ms = event_ms(x_pass, reps, torch)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bytes_per_launch = 32.0 * n_local
+        gbs = bytes_per_launch / t.item() / 1e6
+        sent = 16.0 * n_local * (world - 1) / world  # bytes each GPU stores into its peers per step
+        roofline = {"bound": "hbm", "kernel": "fft_pow2_ext_kernel<512, 8, STRIDED> (local x pass on the received slab, "
+                    "timed alone, max over ranks)", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "avg_launch_ms": t.item(),
+                    "exchange": {"nvlink_bytes_sent_per_gpu_per_step": sent,
+                                 "gbs_per_gpu_over_whole_step": sent / ms_step / 1e6,
+                                 "note": "the z pass stores whole lines into the peers' slabs (sstc_fft_lines_scatter_dev); "
+                                         "measured all-to-all rate of this box: ~590 GB/s per GPU (DESIGN.md 3.4)"}}
     t_load1 = time.time()
 
     # ---- e2e: host arrays in pinned memory, H2D + kernels + D2H inside the timed region ------------------
