@@ -265,7 +265,10 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
     double2 *out_line = nullptr;  // CONTIG line scatter destination
     if (STRIDED) {
         const int64_t tiles_per_plane = (a.inner + C - 1) / C;
-        o = blk / tiles_per_plane;
+        // 32-bit division whenever both fit (always, short of 2^32 tiles): the 64-bit one is ~100 dependent
+        // instructions in front of the first load of every CTA
+        o = ((blk | tiles_per_plane) >> 32) == 0 ? (int64_t) ((uint32_t) blk / (uint32_t) tiles_per_plane)
+                                                  : blk / tiles_per_plane;
         i = (blk - o * tiles_per_plane) * C + c;
         active = i < a.inner;
         in_base = o * a.in_plane + i;
@@ -374,10 +377,17 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
             out_line[t + m * T] = z;
         }
     } else if (a.mode == MODE_C2C) {
+        if (!a.inverse && s == 1.0) {  // the unscaled forward transform: nothing to multiply
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
-            a.out[out_base + (int64_t) (t + m * T) * out_ks] = z;
+            for (int m = 0; m < 8; m++) {
+                a.out[out_base + (int64_t) (t + m * T) * out_ks] = v[m];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                double2 z = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+                a.out[out_base + (int64_t) (t + m * T) * out_ks] = z;
+            }
         }
     } else if (a.mode == MODE_R2C) {
         double2 *hout = a.out + line * (L / 2 + 1);
