@@ -253,6 +253,17 @@ int sstc_svd(const double *src, int64_t nsrc, int src_stride_row, int src_stride
 int sstc_svd_dev(const double *src, int64_t nsrc, int src_stride_row, int src_stride_col, double *u, int64_t nu, double *sv,
         int64_t ns, double *v, int64_t nv, int n_rows, int n_cols, void *stream);
 
+/* eigs (Bindings.cpp:134-137 -> LinearAlgebraOpsEigs.cpp:26-615; ArrayKernel.java:574): eigenvectors `vec` (row-major
+ * size x size, one vector per column; a complex pair occupies two adjacent columns: real part, imaginary part) and
+ * eigenvalues `val` (2 * size doubles, interleaved re / im) of a general real row-major size x size matrix: JAMA's
+ * Hessenberg reduction + double-shift QR + back-substitution, every element updated in the reference's operation
+ * order, so the output is bit-identical to the reference's. src is not modified. Fails with "Invalid arguments" on a
+ * length mismatch and with "Eigenvalue iteration did not converge" where the reference's uncapped hqr2 loop would
+ * never return (an all-zero matrix of size >= 3, NaN input). The device twin synchronises `stream` once. */
+int sstc_eigs(const double *src, int64_t nsrc, double *vec, int64_t nvec, double *val, int64_t nval, int size);
+int sstc_eigs_dev(const double *src, int64_t nsrc, double *vec, int64_t nvec, double *val, int64_t nval, int size,
+        void *stream);
+
 /* find (Bindings.cpp:160-163 -> IndexOps.cpp:26-130): `logical` holds one index per dimension with exactly one -1
  * marking the active dimension; along that line of the int array (as riOp writes it: positions, then -1 padding)
  * *count = number of non-negative entries, and out[0 .. *count) = the first *count entries of the line. `out` must

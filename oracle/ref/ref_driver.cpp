@@ -184,6 +184,13 @@ int sstref_svd(const double *src, int nsrc, int rs, int cs, double *u, int nu, d
     return env_done(env);
 }
 
+int sstref_eigs(const double *src, int nsrc, double *vec, int nvec, double *val, int nval, int size) {
+    JNIEnv *env = env_get();
+    _jobject s = DARR(src, nsrc), ve = DARR(vec, nvec), va = DARR(val, nval);
+    LinearAlgebraOps::eigs(env, 0, &s, &ve, &va, size);
+    return env_done(env);
+}
+
 /* returns the length of the result (copied into out, capacity cap), or -1 on a Java exception */
 int sstref_find(const int *src, int nsrc, const int *sD, const int *sS, int nd, const int *logical, int *out, int cap) {
     JNIEnv *env = env_get();

@@ -135,6 +135,10 @@ class RefKernel:
         self._chk(self._l.sstref_svd(_p(_f64(srcV)), srcV.size, int(srcStrideRow), int(srcStrideCol), _p(_f64(uV)), uV.size,
                                      _p(_f64(sV)), sV.size, _p(_f64(vV)), vV.size, int(nRows), int(nCols)))
 
+    def eigs(self, srcV, vecV, valV, size):
+        self._chk(self._l.sstref_eigs(_p(_f64(srcV)), srcV.size, _p(_f64(vecV)), vecV.size, _p(_f64(valV)), valV.size,
+                                      int(size)))
+
     def find(self, srcV, srcD, srcS, logical):
         sD, sS, lg = _i32(srcD), _i32(srcS), _i32(logical)
         assert srcV.dtype == np.int32

@@ -161,6 +161,10 @@ class CudaArrayKernel:
         _lib.check(self._l.sstc_svd(_vp(srcV), srcV.size, int(srcStrideRow), int(srcStrideCol), _vp(uV), uV.size, _vp(sV),
                                     sV.size, _vp(vV), vV.size, int(nRows), int(nCols)))
 
+    def eigs(self, srcV, vecV, valV, size):
+        """ArrayKernel.eigs (ArrayKernel.java:574; LinearAlgebraOpsEigs.cpp:26-615): bit-identical to the reference."""
+        _lib.check(self._l.sstc_eigs(_vp(srcV), srcV.size, _vp(vecV), vecV.size, _vp(valV), valV.size, int(size)))
+
     def find(self, srcV, srcD, srcS, logical):
         """ArrayKernel.find (ArrayKernel.java:603; IndexOps.java:44-91): returns a new int32 array."""
         if srcV.dtype != np.int32:
@@ -179,7 +183,7 @@ class CudaArrayKernel:
     def _unsupported(self, *args, **kwargs):
         raise NotImplementedError("not provided by the CUDA ArrayKernel (no CPU fallback)")
 
-    eigs = insertSparse = sliceSparse = _unsupported
+    insertSparse = sliceSparse = _unsupported
 
 
 class DeviceArrayKernel:

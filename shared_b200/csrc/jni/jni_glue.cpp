@@ -524,6 +524,20 @@ JNIEXPORT void JNICALL AK(invert)(JNIEnv *env, jobject, jdoubleArray srcV, jdoub
     raise_last(env, rc);
 }
 
+JNIEXPORT void JNICALL AK(eigs)(JNIEnv *env, jobject, jdoubleArray srcV, jdoubleArray vecV, jdoubleArray valV,
+        jint size) {
+    if (!srcV || !vecV || !valV) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize ns = len(env, srcV), nvec = len(env, vecV), nval = len(env, valV);
+    int rc;
+    {
+        Pin s(env, srcV, true), ve(env, vecV, false), va(env, valV, false);
+        rc = sstc_eigs(s.as<double>(), ns, ve.as<double>(), nvec, va.as<double>(), nval, size);
+    }
+    raise_last(env, rc);
+}
+
 JNIEXPORT void JNICALL AK(svd)(JNIEnv *env, jobject, jdoubleArray srcV, jint srcStrideRow, jint srcStrideCol,
         jdoubleArray uV, jdoubleArray sV, jdoubleArray vV, jint nRows, jint nCols) {
     if (!srcV || !uV || !sV || !vV) {

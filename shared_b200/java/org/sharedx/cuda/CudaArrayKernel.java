@@ -10,7 +10,7 @@
  *
  * The sixteen operations on the FFT / array-kernel hot path are native (JNI glue:
  * shared_b200/csrc/jni/jni_glue.cpp, one export per method, same signatures as NativeArrayKernel.java:56-154).
- * Of the interface members outside that path, invert, svd and find are provided; eigs, insertSparse and
+ * Of the interface members outside that path, invert, svd, eigs and find are provided; insertSparse and
  * sliceSparse throw {@link UnsupportedOperationException}: this provider has no CPU fallback.
  */
 package org.sharedx.cuda;
@@ -97,10 +97,12 @@ public class CudaArrayKernel implements ArrayKernel {
     final public native void svd(double[] srcV, int srcStrideRow, int srcStrideCol, //
             double[] uV, double[] sV, double[] vV, int nRows, int nCols);
 
+    /**
+     * JNI: Java_org_sharedx_cuda_CudaArrayKernel_eigs -> sstc_eigs (Hessenberg + double-shift QR in one CTA,
+     * back-substitution with one thread per eigenvalue; bit-identical to the reference's native kernel).
+     */
     @Override
-    public void eigs(double[] srcV, double[] vecV, double[] valV, int size) {
-        throw new UnsupportedOperationException("eigs is not provided by the CUDA ArrayKernel");
-    }
+    final public native void eigs(double[] srcV, double[] vecV, double[] valV, int size);
 
     /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_invert -> sstc_invert (LU with partial pivoting on the GPU). */
     @Override
