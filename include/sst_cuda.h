@@ -274,6 +274,44 @@ int sstc_find(const int32_t *src, int64_t nsrc, const int32_t *sD, const int32_t
 int sstc_find_dev(const int32_t *src, int64_t nsrc, const int32_t *sD, const int32_t *sS, int nd, const int32_t *logical,
         int32_t *out, int32_t *count, void *stream);
 
+/* ---- sparse arrays (Bindings.cpp:165-182 -> SparseOpsInsert.cpp:26-168, SparseOpsSlice.cpp:26-410, SparseOps.cpp:26-260;
+ * ArrayKernel.java:628-674) --------------------------------------------------------------------------------
+ *
+ * Both calls return the four arrays of org.shared.array.sparse.SparseArrayState: `values` (count elements of
+ * elem_bytes), `indices` (count ascending physical indices), `indirection_offsets` (sum(dims) + nd entries: per
+ * dimension the bucket starts of each logical index, closed by count) and `indirections` (nd * count: per dimension the
+ * element positions ordered by logical index, ties in ascending position). The pointers refer to library-owned host
+ * memory that stays valid until the calling thread's next sparse call; the JNI glue copies them into new Java arrays.
+ * elem_bytes: 8 (double[]) or 4 (int[]); the glue serves Object[] by passing positions as 4-byte values and gathering
+ * the references afterwards. Sorting, merging, metadata and value movement run on the device. Bit-exact. */
+typedef struct sstc_sparse_state {
+    int32_t count, n_offsets, n_indirections, elem_bytes;
+    const void *values;
+    const int32_t *indices, *indirection_offsets, *indirections;
+} sstc_sparse_state;
+
+/* insertSparse: merges new (value, physical index) pairs into a sparse array; on equal indices the new value wins.
+ * oldI is ascending without duplicates; newI is in any order and comes back SORTED, as with both reference providers
+ * (SparseOpsInsert.cpp:118-126, SparseOps.java:80-84). oldDo has nd + 1 entries with oldDo[d + 1] - oldDo[d] - 1 ==
+ * oldD[d]. Errors: "Invalid arguments", "Invalid dimensions and/or strides", "Duplicate values are not allowed",
+ * "Invalid physical index", "Invalid array types". */
+int sstc_insert_sparse(int elem_bytes, const void *oldV, int64_t nold, const int32_t *oldD, const int32_t *oldS,
+        const int32_t *oldDo, int nd, const int32_t *oldI, const void *newV, int64_t nnew, int32_t *newI,
+        sstc_sparse_state *out);
+
+/* sliceSparse: `slices` holds nslices3 / 3 triples (source index, destination index, dimension). The destination
+ * cells whose logical index is a sliced destination index in EVERY dimension are cleared; every source element whose
+ * logical index is a sliced source index in every dimension is written to the cross product of the destination
+ * indices its coordinates map to (the lowest source position wins where two collide); the rest of the destination is
+ * kept. srcIo / dstIo (sum(dims) + nd entries) are range-checked for the sliced indices like the reference does;
+ * srcIi / dstIi must be present but the selection is recomputed from the physical indices, so they are not read.
+ * Errors as above plus "Invalid dimension", "Invalid index". */
+int sstc_slice_sparse(int elem_bytes, const int32_t *slices, int nslices3, const void *srcV, int64_t nsrc,
+        const int32_t *srcD, const int32_t *srcS, const int32_t *srcDo, const int32_t *srcI, const int32_t *srcIo,
+        const int32_t *srcIi, const void *dstV, int64_t ndst, const int32_t *dstD, const int32_t *dstS,
+        const int32_t *dstDo, const int32_t *dstI, const int32_t *dstIo, const int32_t *dstIi, int nd,
+        sstc_sparse_state *out);
+
 /* ---- ImageKernel ------------------------------------------------------------------------------------
  *
  * The reference library's second native service (org.shared.image.kernel.ImageKernel,

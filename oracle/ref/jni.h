@@ -169,7 +169,18 @@ struct JNIEnv_ {
     jobject CallObjectMethod(jobject, jmethodID, ...) { return classOf(SHIM_OTHER); }
     void CallStaticVoidMethod(jclass, jmethodID, ...) {}
     void SetStaticBooleanField(jclass, jfieldID, jboolean) {}
-    jobject NewObject(jclass, jmethodID, ...) { return make(SHIM_OTHER, 0, 0, 0); }
+    /* the one constructor the sources call: SparseArrayState(values, indices, indirectionOffsets, indirections)
+     * (NativeArrayKernel.cpp:107); the four array records are kept so that the driver can read them back */
+    jobject NewObject(jclass, jmethodID method, ...) {
+        jobject *fields = (jobject *) calloc(4, sizeof(jobject));
+        va_list ap;
+        va_start(ap, method);
+        for (int i = 0; i < 4; i++) {
+            fields[i] = va_arg(ap, jobject);
+        }
+        va_end(ap);
+        return make(SHIM_OTHER, fields, 4, 1);
+    }
     jint GetIntField(jobject, jfieldID) { return 0; }
     jobject GetObjectField(jobject, jfieldID) { return 0; }
 

@@ -11,6 +11,7 @@
 #include <Bindings.hpp>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <string>
 
@@ -209,6 +210,64 @@ int sstref_find(const int *src, int nsrc, const int *sD, const int *sS, int nd, 
     }
     env_done(env);
     return n;
+}
+
+/* SparseOps (Bindings.cpp:165-182). The SparseArrayState the reference constructs is flattened into caller buffers:
+ * out_counts = {count, n_offsets, n_indirections}; returns 0, 1 on a Java exception, 2 when a buffer is too small. */
+static int sparse_unpack(JNIEnv *env, jobject state, int kind, void *values, int cap_values, int *indices,
+        int *offsets, int cap_offsets, int *indirections, int cap_indirections, int *out_counts) {
+    if (env->pending || !state) {
+        return env_done(env) ? 1 : 1;
+    }
+    jobject *f = (jobject *) state->data;
+    const int count = f[1]->len, noff = f[2]->len, nind = f[3]->len;
+    out_counts[0] = count;
+    out_counts[1] = noff;
+    out_counts[2] = nind;
+    int rc = 0;
+    if (f[0]->len != count || count > cap_values || noff > cap_offsets || nind > cap_indirections) {
+        rc = 2;
+    } else {
+        memcpy(values, f[0]->data, (size_t) count * (kind == SHIM_INT_ARRAY ? 4 : 8));
+        memcpy(indices, f[1]->data, (size_t) count * 4);
+        memcpy(offsets, f[2]->data, (size_t) noff * 4);
+        memcpy(indirections, f[3]->data, (size_t) nind * 4);
+    }
+    for (int i = 0; i < 4; i++) {
+        free(f[i]->data);
+        free(f[i]);
+    }
+    free(f);
+    free(state);
+    env_done(env);
+    return rc;
+}
+
+int sstref_insert_sparse(int kind, const void *oldV, int nold, const int *oldD, const int *oldS, const int *oldDo, int nd,
+        const int *oldI, const void *newV, int nnew, int *newI, void *values, int cap_values, int *indices, int *offsets,
+        int cap_offsets, int *indirections, int cap_indirections, int *out_counts) {
+    JNIEnv *env = env_get();
+    _jobject ov = arr(kind, oldV, nold), od = IARR(oldD, nd), os = IARR(oldS, nd), odo = IARR(oldDo, nd + 1),
+             oi = IARR(oldI, nold), nv = arr(kind, newV, nnew), ni = IARR(newI, nnew);
+    jobject state = SparseOps::insert(env, 0, &ov, &od, &os, &odo, &oi, &nv, &ni);
+    return sparse_unpack(env, state, kind, values, cap_values, indices, offsets, cap_offsets, indirections,
+            cap_indirections, out_counts);
+}
+
+int sstref_slice_sparse(int kind, const int *slices, int nslices3, const void *srcV, int nsrc, const int *srcD,
+        const int *srcS, const int *srcDo, const int *srcI, const int *srcIo, int nsrcIo, const int *srcIi,
+        const void *dstV, int ndst, const int *dstD, const int *dstS, const int *dstDo, const int *dstI, const int *dstIo,
+        int ndstIo, const int *dstIi, int nd, void *values, int cap_values, int *indices, int *offsets, int cap_offsets,
+        int *indirections, int cap_indirections, int *out_counts) {
+    JNIEnv *env = env_get();
+    _jobject sl = IARR(slices, nslices3), sv = arr(kind, srcV, nsrc), sd = IARR(srcD, nd), ss = IARR(srcS, nd),
+             sdo = IARR(srcDo, nd + 1), si = IARR(srcI, nsrc), sio = IARR(srcIo, nsrcIo), sii = IARR(srcIi, nd * nsrc),
+             dv = arr(kind, dstV, ndst), dd = IARR(dstD, nd), ds = IARR(dstS, nd), ddo = IARR(dstDo, nd + 1),
+             di = IARR(dstI, ndst), dio = IARR(dstIo, ndstIo), dii = IARR(dstIi, nd * ndst);
+    jobject state = SparseOps::slice(env, 0, &sl, &sv, &sd, &ss, &sdo, &si, &sio, &sii, &dv, &dd, &ds, &ddo, &di, &dio,
+            &dii);
+    return sparse_unpack(env, state, kind, values, cap_values, indices, offsets, cap_offsets, indirections,
+            cap_indirections, out_counts);
 }
 
 /* NativeImageKernel (Bindings.cpp:144-158) */

@@ -150,6 +150,56 @@ class RefKernel:
             raise RefKernelError(self._l.sstref_last_error().decode())
         return out[:n].copy()
 
+    # -- sparse arrays (ArrayKernel.java:628-674; SparseOpsInsert.cpp, SparseOpsSlice.cpp, SparseOps.cpp) ------
+    # Both return (values, indices, indirectionOffsets, indirections) -- the fields of SparseArrayState.
+    def _sparse_out(self, dtype, cap, nd, dims):
+        cap = max(1, cap)
+        return (np.zeros(cap, dtype=dtype), np.zeros(cap, dtype=np.int32),
+                np.zeros(max(1, int(np.sum(dims)) + nd), dtype=np.int32), np.zeros(max(1, nd * cap), dtype=np.int32),
+                np.zeros(3, dtype=np.int32))
+
+    def _sparse_done(self, rc, out):
+        if rc == 1:
+            raise RefKernelError(self._l.sstref_last_error().decode())
+        assert rc == 0, "oracle buffers too small"
+        v, i, io, ii, counts = out
+        return v[:counts[0]].copy(), i[:counts[0]].copy(), io[:counts[1]].copy(), ii[:counts[2]].copy()
+
+    def insertSparse(self, oldV, oldD, oldS, oldDo, oldI, newV, newI):
+        """newI (an int32 array) is sorted in place, as the reference does (SparseOpsInsert.cpp:118-126)."""
+        oD, oS, oDo, oI = _i32(oldD), _i32(oldS), _i32(oldDo), _i32(oldI)
+        assert newI.dtype == np.int32 and newI.flags.c_contiguous
+        if _kind(oldV) != _kind(newV):
+            raise RefKernelError("Invalid array types")
+        if not (oD.size == oS.size and oDo.size == oD.size + 1 and oI.size == oldV.size and newI.size == newV.size):
+            raise RefKernelError("Invalid arguments")
+        out = self._sparse_out(oldV.dtype, oldV.size + newV.size, oD.size, oD)
+        rc = self._l.sstref_insert_sparse(_kind(oldV), _p(oldV), oldV.size, _p(oD), _p(oS), _p(oDo), oD.size, _p(oI),
+                                          _p(newV), newV.size, _p(newI), _p(out[0]), out[0].size, _p(out[1]), _p(out[2]),
+                                          out[2].size, _p(out[3]), out[3].size, _p(out[4]))
+        return self._sparse_done(rc, out)
+
+    def sliceSparse(self, slices, srcV, srcD, srcS, srcDo, srcI, srcIo, srcIi, dstV, dstD, dstS, dstDo, dstI, dstIo,
+                    dstIi):
+        sl = _i32(slices)
+        sD, sS, sDo, sI, sIo, sIi = (_i32(a) for a in (srcD, srcS, srcDo, srcI, srcIo, srcIi))
+        dD, dS, dDo, dI, dIo, dIi = (_i32(a) for a in (dstD, dstS, dstDo, dstI, dstIo, dstIi))
+        if _kind(srcV) != _kind(dstV):
+            raise RefKernelError("Invalid array types")
+        nd = sD.size
+        if not (sS.size == nd and dD.size == nd and dS.size == nd and sDo.size == nd + 1 and dDo.size == nd + 1 and
+                sI.size == srcV.size and dI.size == dstV.size and sIi.size == nd * srcV.size and
+                dIi.size == nd * dstV.size):
+            raise RefKernelError("Invalid arguments")
+        # the destination slice can hold at most prod(number of destination slices per dimension) new cells
+        cap = dstV.size + int(np.prod([max(1, int(np.sum(sl[2::3] == d))) for d in range(nd)])) if nd else dstV.size + 1
+        out = self._sparse_out(dstV.dtype, cap, nd, dD)
+        rc = self._l.sstref_slice_sparse(_kind(srcV), _p(sl), sl.size, _p(srcV), srcV.size, _p(sD), _p(sS), _p(sDo), _p(sI),
+                                         _p(sIo), sIo.size, _p(sIi), _p(dstV), dstV.size, _p(dD), _p(dS), _p(dDo), _p(dI),
+                                         _p(dIo), dIo.size, _p(dIi), nd, _p(out[0]), out[0].size, _p(out[1]), _p(out[2]),
+                                         out[2].size, _p(out[3]), out[3].size, _p(out[4]))
+        return self._sparse_done(rc, out)
+
     # -- ImageKernel (src/org/shared/image/kernel/ImageKernel.java:56-80) -------------------------------------
     def createIntegralImage(self, srcV, srcD, srcS, dstV, dstD, dstS):
         sD, sS, dD, dS = _i32(srcD), _i32(srcS), _i32(dstD), _i32(dstS)

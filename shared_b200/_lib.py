@@ -91,6 +91,9 @@ SIGNATURES["sstc_svd"] = (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _i64, _vp, _i64
 SIGNATURES["sstc_svd_dev"] = (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _vp])
 SIGNATURES["sstc_eigs"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i])
 SIGNATURES["sstc_eigs_dev"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _vp])
+SIGNATURES["sstc_insert_sparse"] = (ctypes.c_int, [_i, _vp, _i64, c_i32_p, c_i32_p, c_i32_p, _i, _vp, _vp, _i64, _vp, _vp])
+SIGNATURES["sstc_slice_sparse"] = (ctypes.c_int, [_i, c_i32_p, _i, _vp, _i64, c_i32_p, c_i32_p, c_i32_p, _vp, c_i32_p, _vp,
+                                                  _vp, _i64, c_i32_p, c_i32_p, c_i32_p, _vp, c_i32_p, _vp, _i, _vp])
 SIGNATURES["sstc_find"] = (ctypes.c_int, [_vp, _i64, c_i32_p, c_i32_p, _i, c_i32_p, _vp, _i64, c_i32_p])
 SIGNATURES["sstc_find_dev"] = (ctypes.c_int, [_vp, _i64, c_i32_p, c_i32_p, _i, c_i32_p, _vp, c_i32_p, _vp])
 _IMAGE_OPS = {

@@ -6,9 +6,10 @@ NativeArrayKernel (src/org/shared/array/jni/NativeArrayKernel.java:41-154): arra
 int32 arrays standing in for Java double[] / int[], mutated in place where the Java contract mutates them.
 It is the Python twin of shared_b200/java/org/sharedx/cuda/CudaArrayKernel.java; both sit on the host tier of
 include/sst_cuda.h. `DeviceArrayKernel` is the device tier (device pointers + stream) used by bench.py.
-Of the members outside the north-star families, invert, svd and find are provided; eigs, insertSparse and sliceSparse
-raise NotImplementedError -- the Java twin throws UnsupportedOperationException; there is no CPU fallback.
+The members outside the north-star families (invert, svd, eigs, find, insertSparse, sliceSparse) are provided as well;
+everything runs on the GPU -- there is no CPU fallback.
 """
+import collections
 import ctypes
 import time
 
@@ -30,6 +31,17 @@ def _pi(a):
 
 def _vp(a):
     return ctypes.c_void_p(a.ctypes.data)
+
+
+class SparseStateStruct(ctypes.Structure):
+    """sstc_sparse_state (include/sst_cuda.h)."""
+    _fields_ = [("count", ctypes.c_int32), ("n_offsets", ctypes.c_int32), ("n_indirections", ctypes.c_int32),
+                ("elem_bytes", ctypes.c_int32), ("values", ctypes.c_void_p), ("indices", ctypes.c_void_p),
+                ("indirection_offsets", ctypes.c_void_p), ("indirections", ctypes.c_void_p)]
+
+
+# the four fields of org.shared.array.sparse.SparseArrayState (SparseArrayState.java:44-64)
+SparseArrayState = collections.namedtuple("SparseArrayState", "values indices indirectionOffsets indirections")
 
 
 def _check_array(a, name):
@@ -179,11 +191,54 @@ class CudaArrayKernel:
                                      ctypes.byref(count)))
         return line[:count.value].copy()
 
-    # -- outside the north-star op families --------------------------------------------
-    def _unsupported(self, *args, **kwargs):
-        raise NotImplementedError("not provided by the CUDA ArrayKernel (no CPU fallback)")
+    # -- sparse arrays (ArrayKernel.java:628-674) ------------------------------------------------------------------------
+    def _sparse_state(self, st, dtype):
+        def take(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dtype=dt)
+            raw = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(raw, dtype=dt).copy()  # the library reuses its buffers on this thread's next call
+        return SparseArrayState(take(st.values, st.count, dtype), take(st.indices, st.count, np.int32),
+                                take(st.indirection_offsets, st.n_offsets, np.int32),
+                                take(st.indirections, st.n_indirections, np.int32))
 
-    insertSparse = sliceSparse = _unsupported
+    def insertSparse(self, oldV, oldD, oldS, oldDo, oldI, newV, newI):
+        """ArrayKernel.insertSparse (ArrayKernel.java:628-650; SparseOpsInsert.cpp:26-168): returns the new
+        SparseArrayState; newI (an int32 array) comes back sorted, as with both reference providers."""
+        _check_array(oldV, "oldV")
+        _check_array(newV, "newV")
+        if oldV.dtype != newV.dtype:
+            raise _lib.SstCudaError("Invalid array types")
+        oD, oS, oDo, oI = _i32(oldD), _i32(oldS), _i32(oldDo), _i32(oldI)
+        if not (isinstance(newI, np.ndarray) and newI.dtype == np.int32 and newI.flags.c_contiguous):
+            raise _lib.SstCudaError("Invalid array types")
+        if not (oD.size == oS.size and oDo.size == oD.size + 1 and oI.size == oldV.size and newI.size == newV.size):
+            raise _lib.SstCudaError("Invalid arguments")  # SparseOpsInsert.cpp:77-83
+        st = SparseStateStruct()
+        _lib.check(self._l.sstc_insert_sparse(oldV.dtype.itemsize, _vp(oldV), oldV.size, _pi(oD), _pi(oS), _pi(oDo), oD.size,
+                                              _vp(oI), _vp(newV), newV.size, _vp(newI), ctypes.byref(st)))
+        return self._sparse_state(st, oldV.dtype)
+
+    def sliceSparse(self, slices, srcV, srcD, srcS, srcDo, srcI, srcIo, srcIi, dstV, dstD, dstS, dstDo, dstI, dstIo,
+                    dstIi):
+        """ArrayKernel.sliceSparse (ArrayKernel.java:652-674; SparseOpsSlice.cpp:26-410)."""
+        _check_array(srcV, "srcV")
+        _check_array(dstV, "dstV")
+        if srcV.dtype != dstV.dtype:
+            raise _lib.SstCudaError("Invalid array types")
+        sl = _i32(slices)
+        sD, sS, sDo, sI, sIo, sIi = (_i32(a) for a in (srcD, srcS, srcDo, srcI, srcIo, srcIi))
+        dD, dS, dDo, dI, dIo, dIi = (_i32(a) for a in (dstD, dstS, dstDo, dstI, dstIo, dstIi))
+        nd = sD.size
+        if not (sS.size == nd and dD.size == nd and dS.size == nd and sl.size % 3 == 0 and sI.size == srcV.size and
+                dI.size == dstV.size and sDo.size == nd + 1 and dDo.size == nd + 1 and sIi.size == nd * srcV.size and
+                dIi.size == nd * dstV.size and sIo.size == int(sD.sum()) + nd and dIo.size == int(dD.sum()) + nd):
+            raise _lib.SstCudaError("Invalid arguments")  # SparseOpsSlice.cpp:87-98, 128-131
+        st = SparseStateStruct()
+        _lib.check(self._l.sstc_slice_sparse(srcV.dtype.itemsize, _pi(sl), sl.size, _vp(srcV), srcV.size, _pi(sD), _pi(sS),
+                                             _pi(sDo), _vp(sI), _pi(sIo), _vp(sIi), _vp(dstV), dstV.size, _pi(dD), _pi(dS),
+                                             _pi(dDo), _vp(dI), _pi(dIo), _vp(dIi), nd, ctypes.byref(st)))
+        return self._sparse_state(st, srcV.dtype)
 
 
 class DeviceArrayKernel:

@@ -59,6 +59,10 @@ __device__ inline double uniform01(uint64_t key, uint64_t index) {
     return (double) (splitmix64(key ^ splitmix64(index)) >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
 }
 
+// Stable ascending sort of (key, payload) pairs by (key, payload) inside every aligned segment of `seg` pairs
+// (a power of two; `total` a multiple of it): the bitonic network of array_dimension.cu.
+void sort_pairs_segments(uint64_t *keys, int32_t *pay, int64_t total, int64_t seg, cudaStream_t s);
+
 uint64_t next_rng_key();  // advances the library-global call counter (array_elementwise.cu)
 
 // Java Math.max / Math.min semantics (NaN wins, -0.0 < +0.0): ElementOps.java RE_MAX / RE_MIN go through

@@ -1023,6 +1023,11 @@ static void bitonic_sort_segments(uint64_t *keys, int32_t *pay, int64_t total, i
     }
 }
 
+// the same network for other callers (array_sparse.cu): `total` pairs in aligned power-of-two segments of `seg`
+void sort_pairs_segments(uint64_t *keys, int32_t *pay, int64_t total, int64_t seg, cudaStream_t s) {
+    bitonic_sort_segments(keys, pay, total, seg, s);
+}
+
 static void sort_dim(double *in, int32_t *out, const Lines &L, cudaStream_t s) {
     if (L.n_lines == 0 || L.len == 0) {
         return;

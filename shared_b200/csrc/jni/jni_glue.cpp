@@ -583,6 +583,164 @@ JNIEXPORT jintArray JNICALL AK(find)(JNIEnv *env, jobject, jintArray srcV, jintA
     return res;
 }
 
+// ---- sparse arrays (Bindings.cpp:165-182 -> SparseOpsInsert.cpp / SparseOpsSlice.cpp) -------------------------------
+//
+// double[] / int[] values go through the C ABI as they are. Object[] values cannot live in HBM: the same call is made
+// with POSITIONS as 4-byte values (old / destination: 0 .., new / source: n_old ..), and the references are gathered
+// into the result array here -- all index work still happens on the device.
+
+namespace {
+
+// new SparseArrayState(values, indices, indirectionOffsets, indirections): NativeArrayKernel.cpp:103-115
+jobject new_sparse_state(JNIEnv *env, const sstc_sparse_state &st, Kind kind, jobjectArray first, jsize n_first,
+        jobjectArray second) {
+    jobject values = nullptr;
+    if (kind == K_DOUBLE) {
+        jdoubleArray a = env->NewDoubleArray(st.count);
+        if (a && st.count > 0) {
+            env->SetDoubleArrayRegion(a, 0, st.count, static_cast<const jdouble *>(st.values));
+        }
+        values = a;
+    } else if (kind == K_INT) {
+        jintArray a = env->NewIntArray(st.count);
+        if (a && st.count > 0) {
+            env->SetIntArrayRegion(a, 0, st.count, static_cast<const jint *>(st.values));
+        }
+        values = a;
+    } else {
+        // component type of the first array (SparseOps.cpp:96-98: getComponentType(GetObjectClass(oldV)))
+        jclass cls = env->FindClass("java/lang/Class");
+        jmethodID get = cls ? env->GetMethodID(cls, "getComponentType", "()Ljava/lang/Class;") : nullptr;
+        jclass comp = get ? static_cast<jclass>(env->CallObjectMethod(env->GetObjectClass(first), get)) : nullptr;
+        jobjectArray a = comp ? env->NewObjectArray(st.count, comp, nullptr) : nullptr;
+        const int32_t *pos = static_cast<const int32_t *>(st.values);
+        for (jsize i = 0; a && i < st.count; i++) {
+            env->SetObjectArrayElement(a, i, pos[i] < n_first ? env->GetObjectArrayElement(first, pos[i])
+                                                              : env->GetObjectArrayElement(second, pos[i] - n_first));
+        }
+        values = a;
+    }
+    jintArray indices = env->NewIntArray(st.count);
+    jintArray offsets = env->NewIntArray(st.n_offsets);
+    jintArray indirections = env->NewIntArray(st.n_indirections);
+    if (!values || !indices || !offsets || !indirections || env->ExceptionCheck()) {
+        return nullptr;  // OutOfMemoryError pending
+    }
+    if (st.count > 0) {
+        env->SetIntArrayRegion(indices, 0, st.count, reinterpret_cast<const jint *>(st.indices));
+    }
+    if (st.n_offsets > 0) {
+        env->SetIntArrayRegion(offsets, 0, st.n_offsets, reinterpret_cast<const jint *>(st.indirection_offsets));
+    }
+    if (st.n_indirections > 0) {
+        env->SetIntArrayRegion(indirections, 0, st.n_indirections, reinterpret_cast<const jint *>(st.indirections));
+    }
+    jclass cls = env->FindClass("org/shared/array/sparse/SparseArrayState");
+    jmethodID ctor = cls ? env->GetMethodID(cls, "<init>", "(Ljava/lang/Object;[I[I[I)V") : nullptr;
+    return ctor ? env->NewObject(cls, ctor, values, indices, offsets, indirections) : nullptr;
+}
+
+std::vector<int32_t> positions(jsize n, int32_t base) {
+    std::vector<int32_t> v((size_t) (n > 0 ? n : 1));
+    for (jsize i = 0; i < n; i++) {
+        v[(size_t) i] = base + i;
+    }
+    return v;
+}
+
+}  // namespace
+
+JNIEXPORT jobject JNICALL AK(insertSparse)(JNIEnv *env, jobject, jobject oldV, jintArray oldD, jintArray oldS,
+        jintArray oldDo, jintArray oldI, jobject newV, jintArray newI) {
+    if (!oldV || !oldD || !oldS || !oldDo || !oldI || !newV || !newI) {
+        raise(env, "Invalid arguments");
+        return nullptr;
+    }
+    const Kind kind = pair_kind(env, newV, oldV);
+    if (kind == K_BAD) {
+        raise(env, "Invalid array types");
+        return nullptr;
+    }
+    const jsize nd = len(env, oldD), n_old = len(env, static_cast<jarray>(oldV)), n_new = len(env, static_cast<jarray>(newV));
+    if (nd != len(env, oldS) || n_old != len(env, oldI) || n_new != len(env, newI) || nd + 1 != len(env, oldDo)) {
+        raise(env, "Invalid arguments");  // SparseOpsInsert.cpp:77-83
+        return nullptr;
+    }
+    sstc_sparse_state st;
+    int rc;
+    if (kind == K_OBJECT) {
+        const std::vector<int32_t> ov = positions(n_old, 0), nv = positions(n_new, n_old);
+        Pin d(env, oldD, true), s(env, oldS, true), o(env, oldDo, true), oi(env, oldI, true), ni(env, newI, false);
+        rc = sstc_insert_sparse(4, ov.data(), n_old, d.as<int32_t>(), s.as<int32_t>(), o.as<int32_t>(), nd,
+                oi.as<int32_t>(), nv.data(), n_new, ni.as<int32_t>(), &st);
+    } else {
+        Pin ov(env, static_cast<jarray>(oldV), true), nv(env, static_cast<jarray>(newV), true), d(env, oldD, true),
+                s(env, oldS, true), o(env, oldDo, true), oi(env, oldI, true), ni(env, newI, false);
+        rc = sstc_insert_sparse(kind == K_DOUBLE ? 8 : 4, ov.ptr, n_old, d.as<int32_t>(), s.as<int32_t>(), o.as<int32_t>(),
+                nd, oi.as<int32_t>(), nv.ptr, n_new, ni.as<int32_t>(), &st);
+    }
+    if (rc != 0) {
+        raise_last(env, rc);
+        return nullptr;
+    }
+    return new_sparse_state(env, st, kind, static_cast<jobjectArray>(oldV), n_old, static_cast<jobjectArray>(newV));
+}
+
+JNIEXPORT jobject JNICALL AK(sliceSparse)(JNIEnv *env, jobject, jintArray slices, jobject srcV, jintArray srcD,
+        jintArray srcS, jintArray srcDo, jintArray srcI, jintArray srcIo, jintArray srcIi, jobject dstV, jintArray dstD,
+        jintArray dstS, jintArray dstDo, jintArray dstI, jintArray dstIo, jintArray dstIi) {
+    if (!slices || !srcV || !srcD || !srcS || !srcDo || !srcI || !srcIo || !srcIi || !dstV || !dstD || !dstS || !dstDo ||
+            !dstI || !dstIo || !dstIi) {
+        raise(env, "Invalid arguments");
+        return nullptr;
+    }
+    const Kind kind = pair_kind(env, srcV, dstV);
+    if (kind == K_BAD) {
+        raise(env, "Invalid array types");
+        return nullptr;
+    }
+    const jsize nd = len(env, srcD), n_src = len(env, static_cast<jarray>(srcV)), n_dst = len(env, static_cast<jarray>(dstV));
+    const jsize n_sl = len(env, slices);
+    jlong sum_s = 0, sum_d = 0;
+    if (nd == len(env, dstD)) {
+        for (jint v : copy_ints(env, srcD)) {
+            sum_s += v;
+        }
+        for (jint v : copy_ints(env, dstD)) {
+            sum_d += v;
+        }
+    }
+    if (nd != len(env, srcS) || nd != len(env, dstD) || nd != len(env, dstS) || n_sl % 3 != 0 || n_src != len(env, srcI) ||
+            n_dst != len(env, dstI) || nd + 1 != len(env, srcDo) || (jlong) nd * n_src != len(env, srcIi) ||
+            nd + 1 != len(env, dstDo) || (jlong) nd * n_dst != len(env, dstIi) || len(env, srcIo) != sum_s + nd ||
+            len(env, dstIo) != sum_d + nd) {
+        raise(env, "Invalid arguments");  // SparseOpsSlice.cpp:87-98, 128-131
+        return nullptr;
+    }
+    sstc_sparse_state st;
+    int rc;
+    {
+        // the destination plays "old" (positions 0 ..), the source "new" (positions n_dst ..): SparseOpsSlice.cpp:59
+        const std::vector<int32_t> dv = positions(kind == K_OBJECT ? n_dst : 0, 0),
+                                   sv = positions(kind == K_OBJECT ? n_src : 0, n_dst);
+        Pin sl(env, slices, true), sd(env, srcD, true), ss(env, srcS, true), sdo(env, srcDo, true), si(env, srcI, true),
+                sio(env, srcIo, true), sii(env, srcIi, true), dd(env, dstD, true), ds(env, dstS, true), ddo(env, dstDo, true),
+                di(env, dstI, true), dio(env, dstIo, true), dii(env, dstIi, true);
+        Pin pv(env, kind == K_OBJECT ? nullptr : static_cast<jarray>(srcV), true),
+                pd(env, kind == K_OBJECT ? nullptr : static_cast<jarray>(dstV), true);
+        rc = sstc_slice_sparse(kind == K_DOUBLE ? 8 : 4, sl.as<int32_t>(), n_sl,
+                kind == K_OBJECT ? static_cast<const void *>(sv.data()) : pv.ptr, n_src, sd.as<int32_t>(), ss.as<int32_t>(),
+                sdo.as<int32_t>(), si.as<int32_t>(), sio.as<int32_t>(), sii.as<int32_t>(),
+                kind == K_OBJECT ? static_cast<const void *>(dv.data()) : pd.ptr, n_dst, dd.as<int32_t>(), ds.as<int32_t>(),
+                ddo.as<int32_t>(), di.as<int32_t>(), dio.as<int32_t>(), dii.as<int32_t>(), nd, &st);
+    }
+    if (rc != 0) {
+        raise_last(env, rc);
+        return nullptr;
+    }
+    return new_sparse_state(env, st, kind, static_cast<jobjectArray>(dstV), n_dst, static_cast<jobjectArray>(srcV));
+}
+
 // ---- ImageKernel (Bindings.cpp:144-158 -> NativeImageKernel.cpp:32-247) --------------------------------------------
 
 JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaImageKernel_createIntegralImage(JNIEnv *env, jobject,

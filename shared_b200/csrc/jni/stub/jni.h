@@ -54,6 +54,11 @@ struct JNIEnv_ {
     void SetIntArrayRegion(jintArray array, jsize start, jsize len, const jint *buf);
     jobject GetObjectArrayElement(jobjectArray array, jsize index);
     void SetObjectArrayElement(jobjectArray array, jsize index, jobject val);
+    jobjectArray NewObjectArray(jsize len, jclass clazz, jobject init);
+    jclass GetObjectClass(jobject obj);
+    jmethodID GetMethodID(jclass clazz, const char *name, const char *sig);
+    jobject CallObjectMethod(jobject obj, jmethodID methodID, ...);
+    jobject NewObject(jclass clazz, jmethodID methodID, ...);
     jfieldID GetStaticFieldID(jclass clazz, const char *name, const char *sig);
     jmethodID GetStaticMethodID(jclass clazz, const char *name, const char *sig);
     void SetStaticBooleanField(jclass clazz, jfieldID fieldID, jboolean value);

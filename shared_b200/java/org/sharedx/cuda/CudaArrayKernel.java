@@ -10,8 +10,8 @@
  *
  * The sixteen operations on the FFT / array-kernel hot path are native (JNI glue:
  * shared_b200/csrc/jni/jni_glue.cpp, one export per method, same signatures as NativeArrayKernel.java:56-154).
- * Of the interface members outside that path, invert, svd, eigs and find are provided; insertSparse and
- * sliceSparse throw {@link UnsupportedOperationException}: this provider has no CPU fallback.
+ * The interface members outside that path (invert, svd, eigs, find, insertSparse, sliceSparse) are native as well:
+ * every member of the SPI runs on the GPU, and this provider has no CPU fallback.
  */
 package org.sharedx.cuda;
 
@@ -112,19 +112,21 @@ public class CudaArrayKernel implements ArrayKernel {
     @Override
     final public native int[] find(int[] srcV, int[] srcD, int[] srcS, int[] logical);
 
+    /**
+     * JNI: Java_org_sharedx_cuda_CudaArrayKernel_insertSparse -> sstc_insert_sparse (pair sort, scan-ranked merge and
+     * per-dimension metadata on the GPU); the SparseArrayState is constructed by the glue. Object[] values are gathered
+     * on the JVM side from the positions the device computes.
+     */
     @Override
-    public <V> SparseArrayState<V> insertSparse( //
+    final public native <V> SparseArrayState<V> insertSparse( //
             V oldV, int[] oldD, int[] oldS, int[] oldDo, int[] oldI, //
-            V newV, int[] newI) {
-        throw new UnsupportedOperationException("insertSparse is not provided by the CUDA ArrayKernel");
-    }
+            V newV, int[] newI);
 
+    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_sliceSparse -> sstc_slice_sparse. */
     @Override
-    public <V> SparseArrayState<V> sliceSparse(int[] slices, //
+    final public native <V> SparseArrayState<V> sliceSparse(int[] slices, //
             V srcV, int[] srcD, int[] srcS, int[] srcDo, //
             int[] srcI, int[] srcIo, int[] srcIi, //
             V dstV, int[] dstD, int[] dstS, int[] dstDo, //
-            int[] dstI, int[] dstIo, int[] dstIi) {
-        throw new UnsupportedOperationException("sliceSparse is not provided by the CUDA ArrayKernel");
-    }
+            int[] dstI, int[] dstIo, int[] dstIi);
 }

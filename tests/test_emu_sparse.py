@@ -1,0 +1,60 @@
+"""CPU check of the sparse-array pipeline (shared_b200/csrc/sparse_core.cuh -- the orchestration and per-element code
+array_sparse.cu runs on the GPU) under the serial host executor of tests/emu, bit-exact against the reference's own
+SparseOps (golden fixture from oracle/_ref, and the live reference build where present); and of the three phases of the
+executor's scan on 256 host threads per CTA under ThreadSanitizer."""
+import os
+import subprocess
+
+import pytest
+
+import emu_sparse
+import oracle
+import sparse_checks as sc
+
+
+@pytest.fixture(scope="module")
+def build_dir():
+    try:
+        path, log = emu_sparse.build()
+    except RuntimeError as e:
+        pytest.skip(str(e))
+    if not os.path.exists(os.path.join(path, "libsparse_emu.so")):
+        pytest.fail("emulation build failed:\n" + log)
+    return path
+
+
+@pytest.fixture(scope="module")
+def k(build_dir):
+    return emu_sparse.EmuSparseKernel(os.path.join(build_dir, "libsparse_emu.so"))
+
+
+def test_insert_bit_exact(k):
+    assert sc.check_insert_cases(k, oracle.ref()) >= 20
+
+
+def test_slice_bit_exact(k):
+    assert sc.check_slice_cases(k, oracle.ref()) >= 20
+
+
+def test_slice_matches_dense_slicing(k):
+    sc.check_dense_property(k)
+
+
+def test_large_against_numpy_model(k):
+    sc.check_large(k, dims=(48, 40, 32), n_old=20_000, n_new=30_000)
+
+
+def test_errors(k):
+    sc.check_errors(k, emu_sparse.EmuError)
+
+
+def test_scan_phases_on_emulated_ctas(build_dir):
+    fast, tsan = os.path.join(build_dir, "scan_emu_fast"), os.path.join(build_dir, "scan_emu_tsan")
+    for n in (0, 1, 7, 2047, 2048, 2049, 4096, 100_000, 1_500_000):
+        assert subprocess.run([fast, str(n), "11"], capture_output=True, timeout=300).returncode == 0, n
+    if not os.path.exists(tsan):
+        pytest.skip("ThreadSanitizer runtime not installed")
+    for n in (5, 2049, 9000):
+        res = subprocess.run([tsan, str(n), "3"], capture_output=True, text=True, timeout=600)
+        assert "ThreadSanitizer" not in res.stderr, res.stderr[:3000]
+        assert res.returncode == 0, n
