@@ -296,3 +296,11 @@ def smoke_check():
     out = np.zeros(15)
     k.rrOp(0, a, [3, 4, 5], [20, 5, 1], out, [3, 1, 5], [5, 5, 1], 1)  # RealArrayTest.java:726-758
     assert np.array_equal(out, a.reshape(3, 4, 5).sum(1).ravel())
+    m = np.array([[2.0, 0, 0], [0, 0, -1], [0, 1, 0]])  # eigenvalues 2, +-i
+    vec, val = np.zeros(9), np.zeros(6)
+    k.eigs(m.ravel().copy(), vec, val, 3)
+    assert sorted(val[0::2].tolist()) == [0.0, 0.0, 2.0] and sorted(val[1::2].tolist()) == [-1.0, 0.0, 1.0]
+    st = k.insertSparse(np.zeros(0), [2, 3], [3, 1], [0, 3, 7], np.zeros(0, dtype=np.int32), np.array([5.0, 4.0]),
+                        np.array([4, 1], dtype=np.int32))
+    assert np.array_equal(st.indices, [1, 4]) and np.array_equal(st.values, [4.0, 5.0])
+    assert np.array_equal(st.indirectionOffsets, [0, 1, 2, 0, 0, 2, 2]) and np.array_equal(st.indirections, [0, 1, 0, 1])
