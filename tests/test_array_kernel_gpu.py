@@ -512,8 +512,6 @@ def test_error_messages(k):
         k.eOp(0, np.zeros(3), np.zeros(4), np.zeros(3), False)
     with pytest.raises(E, match="Invalid array types"):  # ObjectArrayTest.java:289-305
         k.map([0, 0, 1], np.zeros(1), [1], [1], np.zeros(1, dtype=np.int32), [1], [1])
-    with pytest.raises(NotImplementedError):
-        k.eigs()
 
 
 def test_rng_ops_statistics(k):
