@@ -3,9 +3,11 @@
 //
 // The arithmetic lives in eigs_core.cuh (shared with the host emulation the CPU tests run under ThreadSanitizer);
 // this file holds the three launches and the two entry points:
-//   1. eigs_schur_kernel     ONE CTA: Hessenberg reduction + accumulation + double-shift QR. The working matrix sits
-//                            in shared memory (row stride padded to an odd count, so walking a row and walking a
-//                            column are both bank-conflict free) when size <= 158, else in its HBM buffer.
+//   1. eigs_schur_kernel     ONE CTA: Hessenberg reduction + accumulation, then the double-shift QR on H alone (its
+//                            steps are recorded), then the recorded steps applied to V. The working matrix sits in
+//                            shared memory (row stride padded to an odd count, so walking a row and walking a column
+//                            are both bank-conflict free) when size <= 158, and V takes its place there for the last
+//                            stage; larger matrices work in their HBM buffers.
 //   2. eigs_backsub_kernel   one thread per eigenvalue: back-substitution against the read-only Schur form.
 //   3. eigs_backtransform_kernel  one thread per element of vec = V X.
 // Built with -fmad=false (Makefile NOFMA): with every element updated in the reference's operation order the output is
@@ -21,15 +23,18 @@ namespace sstc {
 struct DevCta {
     int tid, nthreads;
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void atomic_max(int *p, int v) { atomicMax(p, v); }
 };
 
 constexpr int kEigsMaxThreads = 512;
-constexpr int64_t kEigsSmemBudget = 200 * 1024;  // of the 227 KB a CTA may opt into
+constexpr int64_t kEigsSmemBudget = 200 * 1024;  // dynamic; + 12 KB of static staging, of the 227 KB a CTA may opt into
+constexpr int kEigsChunk = 256;                  // recorded steps staged per pass over V
 
 __global__ void __launch_bounds__(kEigsMaxThreads) eigs_schur_kernel(const double *__restrict__ src, double *T,
-        double *V, double *val, double *ort, double *norm, int *status, int n, int in_smem) {
+        double *V, double *val, double *ort, double *norm, int *status, EigsRot *log, int log_cap, int n, int in_smem) {
     extern __shared__ double s_h[];
     __shared__ EigsShared sh;
+    __shared__ EigsRot chunk[kEigsChunk];
     DevCta cta{(int) threadIdx.x, (int) blockDim.x};
     double *H = in_smem ? s_h : T;
     const int ld = in_smem ? (n | 1) : n;
@@ -39,15 +44,28 @@ __global__ void __launch_bounds__(kEigsMaxThreads) eigs_schur_kernel(const doubl
     cta.sync();
     eigs_hessenberg(cta, H, ld, V, ort, n, &sh);
     cta.sync();
-    eigs_schur(cta, H, ld, V, val, n, &sh, norm);
+    const int pending = eigs_schur(cta, H, ld, V, val, n, &sh, norm, log, log_cap, chunk, kEigsChunk);  // uniform
     cta.sync();
     if (cta.tid == 0) {
-        *status = sh.mode == EIGS_FAILED;
+        *status = pending < 0;
     }
     if (in_smem) {
         for (int e = cta.tid; e < n * n; e += cta.nthreads) {
             T[e] = H[(e / n) * ld + e % n];
         }
+        cta.sync();
+        if (pending > 0) {  // V takes H's place in shared memory, the recorded steps are applied, V goes back
+            for (int e = cta.tid; e < n * n; e += cta.nthreads) {
+                s_h[(e / n) * ld + e % n] = V[e];
+            }
+            cta.sync();
+            eigs_apply_rots(cta, s_h, ld, n, log, pending, chunk, kEigsChunk);
+            for (int e = cta.tid; e < n * n; e += cta.nthreads) {
+                V[e] = s_h[(e / n) * ld + e % n];
+            }
+        }
+    } else if (pending > 0) {
+        eigs_apply_rots(cta, V, n, n, log, pending, chunk, kEigsChunk);
     }
 }
 
@@ -74,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) eigs_backtransform_kernel(const doub
     }
 }
 
-static thread_local Scratch t_eigs_t, t_eigs_v, t_eigs_x, t_eigs_small;
+static thread_local Scratch t_eigs_t, t_eigs_v, t_eigs_x, t_eigs_small, t_eigs_log;
 
 }  // namespace sstc
 
@@ -108,9 +126,13 @@ int sstc_eigs_dev(const double *src, int64_t nsrc, double *vec, int64_t nvec, do
             SSTC_CUDA(cudaFuncSetAttribute(eigs_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                     (int) kEigsSmemBudget));
         }
+        // room for the recorded QR steps (about 1.5 n^2 of them on random input); a full log is applied on the way
+        const int log_cap = (int) std::min<int64_t>(std::max<int64_t>(8 * n2, 4096), 1 << 21);
+        EigsRot *log = static_cast<EigsRot *>(t_eigs_log.get((int64_t) log_cap * (int64_t) sizeof(EigsRot)));
         const int threads = std::min(kEigsMaxThreads, std::max(32, (n + 31) / 32 * 32));
         SSTC_CUDA(cudaMemsetAsync(X, 0, (size_t) n2 * 8, s));
-        eigs_schur_kernel<<<1, threads, in_smem ? (size_t) smem : 0, s>>>(src, T, V, val, ort, norm, status, n, in_smem);
+        eigs_schur_kernel<<<1, threads, in_smem ? (size_t) smem : 0, s>>>(src, T, V, val, ort, norm, status, log, log_cap,
+                n, in_smem);
         check_launch("eigs_schur_kernel");
         eigs_backsub_kernel<<<(n + 31) / 32, 32, 0, s>>>(T, X, val, norm, status, n);
         check_launch("eigs_backsub_kernel");

@@ -5,10 +5,15 @@
 // nonsymmetric path: Householder reduction to Hessenberg form (orthes / ortran), Francis double-shift QR to the real
 // Schur form (hqr2), back-substitution and back-transformation. The reference runs it as one scalar loop nest; here
 // the same arithmetic is cut into phases of one cooperative thread array:
-//   * whatever is a chain of dependent scalars (deflation search, shifts, the search for two small sub-diagonal
-//     elements, the Householder vector of a column) is done by thread 0 and broadcast through EigsShared;
-//   * every similarity update is done with ONE THREAD PER COLUMN (row modifications) or ONE THREAD PER ROW (column
-//     modifications, accumulation into V), each thread walking its column/row in the reference's order.
+//   * chains of dependent scalars (the Householder vector of a column, root extraction, shifts) are done by thread 0
+//     and broadcast through EigsShared;
+//   * the two searches that open a QR sweep (a small sub-diagonal element; two consecutive small ones) are sets of
+//     independent tests: every thread tests its own indices and the largest hit wins (atomic max);
+//   * every similarity update of H is done with ONE THREAD PER COLUMN (row modifications) or ONE THREAD PER ROW
+//     (column modifications), each thread walking its column/row in the reference's order;
+//   * the QR iteration never reads V, so its steps are only RECORDED while it runs (EigsRot) and applied to V
+//     afterwards with one thread per row of V walking the log front to back -- no barrier per step, and V can take
+//     H's place in shared memory once H is done.
 // So every matrix element sees exactly the reference's sequence of IEEE operations (the file is compiled without FMA
 // contraction): the result is bit-identical to LinearAlgebraOpsEigs.cpp, which the parity tests assert.
 //   * back-substitution: the eigenvector of eigenvalue n only reads the Schur form's columns <= n and writes column n
@@ -16,7 +21,8 @@
 //     matrix X all columns are independent: one thread per eigenvalue (eigs_backsub_column);
 //   * back-transformation vec = V X (upper triangular X): one thread per output element.
 //
-// The Cta parameter supplies tid / nthreads / sync(): threadIdx.x / blockDim.x / __syncthreads() on the device
+// The Cta parameter supplies tid / nthreads / sync() / atomic_max(): threadIdx.x / blockDim.x / __syncthreads() /
+// atomicMax() on the device
 // (array_eigs.cu), a pthread barrier in tests/emu/eigs_emu.cpp, where the same code runs under ThreadSanitizer so
 // that a missing barrier shows up as a data race on the CPU.
 #pragma once
@@ -32,7 +38,7 @@
 
 namespace sstc {
 
-enum : int { EIGS_DONE = 0, EIGS_REAL_PAIR = 1, EIGS_QR_SWEEP = 2, EIGS_FAILED = 3 };
+enum : int { EIGS_DONE = 0, EIGS_REAL_PAIR = 1, EIGS_QR_SWEEP = 2, EIGS_FAILED = 3, EIGS_NEXT = 4 };
 
 // hqr2 as the reference has it never gives up ("Could check iteration count here", LinearAlgebraOpsEigs.cpp:330): on
 // an all-zero matrix of size >= 3 or on NaN input it spins forever. A kernel must not, so a root that has not
@@ -42,9 +48,11 @@ constexpr int kEigsMaxSweepsPerRoot = 1000;
 
 // Broadcast slots: written by thread 0 in its scalar phase, read by everybody after the next barrier.
 struct EigsShared {
-    double p, q, r, x;  // rotation / first Householder vector of a sweep, the shift x (hqr2's stale-x test)
+    double p, q;        // plane rotation of a real pair
+    double x, y, w;     // the shift of a sweep
+    double norm;
     double hacc;        // orthes: the Householder scalar h; 0 when the column is already zero
-    int mode, l, m, n;
+    int mode, l, m, n;  // l, m: targets of the atomic-max searches; n: index of the root being isolated
 };
 
 SSTC_HD inline double eigs_eps() { return 2.220446049250313e-16; }  // pow(2.0, -52.0)
@@ -146,92 +154,158 @@ SSTC_HD inline void eigs_hessenberg(Cta &cta, double *H, int ld, double *V, doub
     }
 }
 
-// LinearAlgebraOpsEigs.cpp:165-453 (hqr2 up to, not including, the back-substitution). On return H holds the real
-// Schur form, V the accumulated transformations, val the interleaved (re, im) eigenvalues; *norm_out the norm
-// hqr2 computes first (thread 0 writes it). sh->mode is EIGS_DONE or EIGS_FAILED afterwards.
+// One similarity step of hqr2 as it acts on V: recorded by thread 0 while the QR iteration runs on H alone, applied to
+// V afterwards (eigs_apply_rots). 48 bytes.
+struct EigsRot {
+    double x, y, z, q, r;  // EIGS_ROT_PLANE: x = p, y = q of the plane rotation
+    int32_t k, kind;
+};
+enum : int { EIGS_ROT_QR3 = 0, EIGS_ROT_QR2 = 1, EIGS_ROT_PLANE = 2 };
+
+// V <- V * (the recorded steps, in order): one thread per ROW of V, every row walking the log front to back, so each
+// element sees the reference's operation order (LinearAlgebraOpsEigs.cpp:284-290, 437-447). The log is staged through
+// `chunk` (shared memory on the device) chunk_cap entries at a time. Ends with a barrier.
 template <class Cta>
-SSTC_HD inline void eigs_schur(Cta &cta, double *H, int ld, double *V, double *val, int nn, EigsShared *sh,
-        double *norm_out) {
+SSTC_HD inline void eigs_apply_rots(Cta &cta, double *V, int ldv, int nn, const EigsRot *log, int count, EigsRot *chunk,
+        int chunk_cap) {
+    const int tid = cta.tid, nt = cta.nthreads;
+    for (int base = 0; base < count; base += chunk_cap) {
+        const int m = count - base < chunk_cap ? count - base : chunk_cap;
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(log + base);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(chunk);
+        for (int w = tid; w < m * 6; w += nt) {
+            dst[w] = src[w];
+        }
+        cta.sync();
+        for (int i = tid; i < nn; i += nt) {
+            double *row = V + (int64_t) i * ldv;
+            for (int t = 0; t < m; t++) {
+                const EigsRot &e = chunk[t];
+                const int k = e.k;
+                if (e.kind == EIGS_ROT_PLANE) {
+                    const double z = row[k];
+                    row[k] = e.y * z + e.x * row[k + 1];
+                    row[k + 1] = e.y * row[k + 1] - e.x * z;
+                } else {
+                    double p = e.x * row[k] + e.y * row[k + 1];
+                    if (e.kind == EIGS_ROT_QR3) {
+                        p = p + e.z * row[k + 2];
+                        row[k + 2] = row[k + 2] - p * e.r;
+                    }
+                    row[k] = row[k] - p;
+                    row[k + 1] = row[k + 1] - p * e.q;
+                }
+            }
+        }
+        cta.sync();
+    }
+}
+
+// LinearAlgebraOpsEigs.cpp:165-453 (hqr2 up to, not including, the back-substitution), on H alone. On return H holds
+// the real Schur form, val the interleaved (re, im) eigenvalues, *norm_out the norm hqr2 computes first, and log[0 ..
+// return value) the steps still to be applied to V (eigs_apply_rots); when the log fills up on the way it is applied
+// to V (row stride nn) and restarted. Returns -1 when a root does not converge (EIGS_FAILED).
+//   per sweep: the search for a small sub-diagonal element and the search for two consecutive small ones are each a
+//   set of independent tests, so every thread tests its own indices and the largest hit wins (atomic max) instead of
+//   thread 0 walking down the diagonal; thread 0 then does the scalar branch work (roots, shifts) and all threads run
+//   the bulge chase: row modification with one thread per column, barrier, column modification with one thread per
+//   row, barrier.
+template <class Cta>
+SSTC_HD inline int eigs_schur(Cta &cta, double *H, int ld, double *V, double *val, int nn, EigsShared *sh,
+        double *norm_out, EigsRot *log, int log_cap, EigsRot *chunk, int chunk_cap) {
     const int tid = cta.tid, nt = cta.nthreads;
     const double eps = eigs_eps();
+    int log_n = 0;  // uniform: every thread counts the recorded steps
     // thread 0's private state
-    int n = nn - 1, iter = 0;
-    double exshift = 0.0, norm = 0.0;
+    int iter = 0;
+    double exshift = 0.0;
     if (tid == 0) {
+        double norm = 0.0;
         for (int i = 0; i < nn; i++) {
             for (int j = (i - 1 > 0 ? i - 1 : 0); j < nn; j++) {
                 norm = norm + fabs(H[i * ld + j]);
             }
         }
         *norm_out = norm;
+        sh->norm = norm;
+        sh->n = nn - 1;
+        sh->l = 0;
     }
+    cta.sync();
+    const double norm = sh->norm;
     for (;;) {
+        const int n = sh->n;
+        if (n < 0) {
+            return log_n;
+        }
+        // look for a single small sub-diagonal element: the largest l in [1, n] that passes, else 0
+        for (int l = 1 + tid; l <= n; l += nt) {
+            double s = fabs(H[(l - 1) * ld + (l - 1)]) + fabs(H[l * ld + l]);
+            if (s == 0.0) {
+                s = norm;
+            }
+            if (fabs(H[l * ld + (l - 1)]) < eps * s) {
+                cta.atomic_max(&sh->l, l);
+            }
+        }
+        cta.sync();
         if (tid == 0) {
-            int mode = EIGS_DONE;
-            while (n >= 0) {
-                double s, w, x, y, z, p, q, r;
-                int l = n;
-                while (l > 0) {
-                    s = fabs(H[(l - 1) * ld + (l - 1)]) + fabs(H[l * ld + l]);
-                    if (s == 0.0) {
-                        s = norm;
+            const int l = sh->l;
+            int mode = EIGS_NEXT;
+            double s, w, x, y, z, p, q, r;
+            if (l == n) {  // one root found
+                H[n * ld + n] = H[n * ld + n] + exshift;
+                val[2 * n] = H[n * ld + n];
+                val[2 * n + 1] = 0.0;
+                sh->n = n - 1;
+                iter = 0;
+            } else if (l == n - 1) {  // two roots found
+                w = H[n * ld + (n - 1)] * H[(n - 1) * ld + n];
+                p = (H[(n - 1) * ld + (n - 1)] - H[n * ld + n]) / 2.0;
+                q = p * p + w;
+                z = sqrt(fabs(q));
+                H[n * ld + n] = H[n * ld + n] + exshift;
+                H[(n - 1) * ld + (n - 1)] = H[(n - 1) * ld + (n - 1)] + exshift;
+                x = H[n * ld + n];
+                if (q >= 0) {  // real pair: a plane rotation of rows / columns n-1, n follows
+                    if (p >= 0) {
+                        z = p + z;
+                    } else {
+                        z = p - z;
                     }
-                    if (fabs(H[l * ld + (l - 1)]) < eps * s) {
-                        break;
+                    val[2 * (n - 1)] = x + z;
+                    val[2 * n] = val[2 * (n - 1)];
+                    if (z != 0.0) {
+                        val[2 * n] = x - w / z;
                     }
-                    l--;
-                }
-                if (l == n) {  // one root found
-                    H[n * ld + n] = H[n * ld + n] + exshift;
-                    val[2 * n] = H[n * ld + n];
+                    val[2 * (n - 1) + 1] = 0.0;
                     val[2 * n + 1] = 0.0;
-                    n--;
-                    iter = 0;
-                    continue;
-                }
-                if (l == n - 1) {  // two roots found
-                    w = H[n * ld + (n - 1)] * H[(n - 1) * ld + n];
-                    p = (H[(n - 1) * ld + (n - 1)] - H[n * ld + n]) / 2.0;
-                    q = p * p + w;
-                    z = sqrt(fabs(q));
-                    H[n * ld + n] = H[n * ld + n] + exshift;
-                    H[(n - 1) * ld + (n - 1)] = H[(n - 1) * ld + (n - 1)] + exshift;
-                    x = H[n * ld + n];
-                    if (q >= 0) {  // real pair: a plane rotation of rows / columns n-1, n follows
-                        if (p >= 0) {
-                            z = p + z;
-                        } else {
-                            z = p - z;
-                        }
-                        val[2 * (n - 1)] = x + z;
-                        val[2 * n] = val[2 * (n - 1)];
-                        if (z != 0.0) {
-                            val[2 * n] = x - w / z;
-                        }
-                        val[2 * (n - 1) + 1] = 0.0;
-                        val[2 * n + 1] = 0.0;
-                        x = H[n * ld + (n - 1)];
-                        s = fabs(x) + fabs(z);
-                        p = x / s;
-                        q = z / s;
-                        r = sqrt(p * p + q * q);
-                        sh->p = p / r;
-                        sh->q = q / r;
-                        sh->n = n;
-                        mode = EIGS_REAL_PAIR;
-                        n = n - 2;
-                        iter = 0;
-                        break;
-                    }
-                    val[2 * (n - 1)] = x + p;  // complex pair
+                    x = H[n * ld + (n - 1)];
+                    s = fabs(x) + fabs(z);
+                    p = x / s;
+                    q = z / s;
+                    r = sqrt(p * p + q * q);
+                    p = p / r;
+                    q = q / r;
+                    sh->p = p;
+                    sh->q = q;
+                    sh->m = n;  // the pair's upper index
+                    EigsRot &e = log[log_n];
+                    e.x = p;
+                    e.y = q;
+                    e.z = e.q = e.r = 0.0;
+                    e.k = n - 1;
+                    e.kind = EIGS_ROT_PLANE;
+                    mode = EIGS_REAL_PAIR;
+                } else {  // complex pair
+                    val[2 * (n - 1)] = x + p;
                     val[2 * n] = x + p;
                     val[2 * (n - 1) + 1] = z;
                     val[2 * n + 1] = -z;
-                    n = n - 2;
-                    iter = 0;
-                    continue;
                 }
-                // no convergence yet: form the shift
+                sh->n = n - 2;
+                iter = 0;
+            } else {  // no convergence yet: form the shift
                 x = H[n * ld + n];
                 y = H[(n - 1) * ld + (n - 1)];  // l < n always holds here
                 w = H[n * ld + (n - 1)] * H[(n - 1) * ld + n];
@@ -263,57 +337,29 @@ SSTC_HD inline void eigs_schur(Cta &cta, double *H, int ld, double *V, double *v
                 iter = iter + 1;
                 if (iter > kEigsMaxSweepsPerRoot) {
                     mode = EIGS_FAILED;
-                    break;
+                } else {
+                    sh->x = x;
+                    sh->y = y;
+                    sh->w = w;
+                    sh->m = l;  // floor of the search below
+                    mode = EIGS_QR_SWEEP;
                 }
-                // look for two consecutive small sub-diagonal elements
-                int m = n - 2;
-                p = q = r = 0.0;
-                while (m >= l) {
-                    z = H[m * ld + m];
-                    r = x - z;
-                    s = y - z;
-                    p = (r * s - w) / H[(m + 1) * ld + m] + H[m * ld + (m + 1)];
-                    q = H[(m + 1) * ld + (m + 1)] - z - r - s;
-                    r = H[(m + 2) * ld + (m + 1)];
-                    s = fabs(p) + fabs(q) + fabs(r);
-                    p = p / s;
-                    q = q / s;
-                    r = r / s;
-                    if (m == l) {
-                        break;
-                    }
-                    if (fabs(H[m * ld + (m - 1)]) * (fabs(q) + fabs(r)) <
-                            eps * (fabs(p) * (fabs(H[(m - 1) * ld + (m - 1)]) + fabs(z) +
-                                                     fabs(H[(m + 1) * ld + (m + 1)])))) {
-                        break;
-                    }
-                    m--;
-                }
-                for (int i = m + 2; i <= n; i++) {
-                    H[i * ld + (i - 2)] = 0.0;
-                    if (i > m + 2) {
-                        H[i * ld + (i - 3)] = 0.0;
-                    }
-                }
-                sh->p = p;
-                sh->q = q;
-                sh->r = r;
-                sh->x = x;
-                sh->l = l;
-                sh->m = m;
-                sh->n = n;
-                mode = EIGS_QR_SWEEP;
-                break;
+            }
+            if (mode != EIGS_QR_SWEEP) {
+                sh->l = 0;  // nobody else reads it in these modes; ready for the next search
             }
             sh->mode = mode;
         }
         cta.sync();
         const int mode = sh->mode;
-        if (mode == EIGS_DONE || mode == EIGS_FAILED) {
-            break;  // sh->mode keeps the outcome for the caller
+        if (mode == EIGS_FAILED) {
+            return -1;
+        }
+        if (mode == EIGS_NEXT) {
+            continue;
         }
         if (mode == EIGS_REAL_PAIR) {
-            const int n2 = sh->n;
+            const int n2 = sh->m;
             const double p = sh->p, q = sh->q;
             for (int j = n2 - 1 + tid; j < nn; j += nt) {  // row modification
                 const double z = H[(n2 - 1) * ld + j];
@@ -321,25 +367,61 @@ SSTC_HD inline void eigs_schur(Cta &cta, double *H, int ld, double *V, double *v
                 H[n2 * ld + j] = q * H[n2 * ld + j] - p * z;
             }
             cta.sync();
-            for (int i = tid; i < nn; i += nt) {
-                if (i <= n2) {  // column modification
-                    const double z = H[i * ld + (n2 - 1)];
-                    H[i * ld + (n2 - 1)] = q * z + p * H[i * ld + n2];
-                    H[i * ld + n2] = q * H[i * ld + n2] - p * z;
+            for (int i = tid; i <= n2; i += nt) {  // column modification
+                const double z = H[i * ld + (n2 - 1)];
+                H[i * ld + (n2 - 1)] = q * z + p * H[i * ld + n2];
+                H[i * ld + n2] = q * H[i * ld + n2] - p * z;
+            }
+            log_n++;  // thread 0 recorded the rotation before the barrier above
+            cta.sync();
+        } else {
+            // look for two consecutive small sub-diagonal elements: the largest m in (l, n-2] that passes, else l
+            const int l = sh->l;
+            const double sx = sh->x, sy = sh->y, sw = sh->w;
+            for (int m = l + 1 + tid; m <= n - 2; m += nt) {
+                const double z = H[m * ld + m];
+                double r = sx - z;
+                double s = sy - z;
+                double p = (r * s - sw) / H[(m + 1) * ld + m] + H[m * ld + (m + 1)];
+                double q = H[(m + 1) * ld + (m + 1)] - z - r - s;
+                r = H[(m + 2) * ld + (m + 1)];
+                s = fabs(p) + fabs(q) + fabs(r);
+                p = p / s;
+                q = q / s;
+                r = r / s;
+                if (fabs(H[m * ld + (m - 1)]) * (fabs(q) + fabs(r)) <
+                        eps * (fabs(p) * (fabs(H[(m - 1) * ld + (m - 1)]) + fabs(z) + fabs(H[(m + 1) * ld + (m + 1)])))) {
+                    cta.atomic_max(&sh->m, m);
                 }
-                const double z = V[i * nn + (n2 - 1)];  // accumulate transformations
-                V[i * nn + (n2 - 1)] = q * z + p * V[i * nn + n2];
-                V[i * nn + n2] = q * V[i * nn + n2] - p * z;
             }
             cta.sync();
-            continue;
-        }
-        // double QR step involving rows l:n and columns m:n; every thread tracks the scalars redundantly
-        {
-            const int l = sh->l, m = sh->m, n2 = sh->n;
-            double p = sh->p, q = sh->q, r = sh->r, x = sh->x, y, z, s;
-            for (int k = m; k <= n2 - 1; k++) {
-                const bool not_last = (k != n2 - 1);
+            const int m = sh->m;
+            if (tid == 0) {
+                sh->l = 0;  // everybody read it before the barrier above; the next search is barriers away
+            }
+            double p, q, r, x = sx, y, z, s;
+            {
+                z = H[m * ld + m];
+                r = sx - z;
+                s = sy - z;
+                p = (r * s - sw) / H[(m + 1) * ld + m] + H[m * ld + (m + 1)];
+                q = H[(m + 1) * ld + (m + 1)] - z - r - s;
+                r = H[(m + 2) * ld + (m + 1)];
+                s = fabs(p) + fabs(q) + fabs(r);
+                p = p / s;
+                q = q / s;
+                r = r / s;
+            }
+            for (int i = m + 2 + tid; i <= n; i += nt) {
+                H[i * ld + (i - 2)] = 0.0;
+                if (i > m + 2) {
+                    H[i * ld + (i - 3)] = 0.0;
+                }
+            }
+            cta.sync();
+            // double QR step involving rows l:n and columns m:n; every thread tracks the scalars redundantly
+            for (int k = m; k <= n - 1; k++) {
+                const bool not_last = (k != n - 1);
                 if (k != m) {
                     p = H[k * ld + (k - 1)];
                     q = H[(k + 1) * ld + (k - 1)];
@@ -382,30 +464,38 @@ SSTC_HD inline void eigs_schur(Cta &cta, double *H, int ld, double *V, double *v
                         } else if (l != m) {
                             H[k * ld + (k - 1)] = -H[k * ld + (k - 1)];
                         }
+                        EigsRot &e = log[log_n];  // what this step does to V
+                        e.x = x;
+                        e.y = y;
+                        e.z = z;
+                        e.q = q;
+                        e.r = r;
+                        e.k = k;
+                        e.kind = not_last ? EIGS_ROT_QR3 : EIGS_ROT_QR2;
                     }
-                    const int ilast = n2 < k + 3 ? n2 : k + 3;
-                    for (int i = tid; i < nn; i += nt) {
-                        if (i <= ilast) {  // column modification
-                            double t = x * H[i * ld + k] + y * H[i * ld + (k + 1)];
-                            if (not_last) {
-                                t = t + z * H[i * ld + (k + 2)];
-                                H[i * ld + (k + 2)] = H[i * ld + (k + 2)] - t * r;
-                            }
-                            H[i * ld + k] = H[i * ld + k] - t;
-                            H[i * ld + (k + 1)] = H[i * ld + (k + 1)] - t * q;
-                        }
-                        double t = x * V[i * nn + k] + y * V[i * nn + (k + 1)];  // accumulate transformations
+                    const int ilast = n < k + 3 ? n : k + 3;
+                    for (int i = tid; i <= ilast; i += nt) {  // column modification
+                        double t = x * H[i * ld + k] + y * H[i * ld + (k + 1)];
                         if (not_last) {
-                            t = t + z * V[i * nn + (k + 2)];
-                            V[i * nn + (k + 2)] = V[i * nn + (k + 2)] - t * r;
+                            t = t + z * H[i * ld + (k + 2)];
+                            H[i * ld + (k + 2)] = H[i * ld + (k + 2)] - t * r;
                         }
-                        V[i * nn + k] = V[i * nn + k] - t;
-                        V[i * nn + (k + 1)] = V[i * nn + (k + 1)] - t * q;
+                        H[i * ld + k] = H[i * ld + k] - t;
+                        H[i * ld + (k + 1)] = H[i * ld + (k + 1)] - t * q;
                     }
+                    log_n++;
                     cta.sync();
+                    if (log_n == log_cap) {  // uniform
+                        eigs_apply_rots(cta, V, nn, nn, log, log_n, chunk, chunk_cap);
+                        log_n = 0;
+                    }
                 }
             }
             cta.sync();  // nobody still reads *sh when thread 0 starts its next scalar phase
+        }
+        if (log_n == log_cap) {  // a plane rotation filled the log
+            eigs_apply_rots(cta, V, nn, nn, log, log_n, chunk, chunk_cap);
+            log_n = 0;
         }
     }
 }

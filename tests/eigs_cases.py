@@ -6,10 +6,9 @@ import numpy as np
 
 
 def cases(sizes=(1, 2, 3, 5, 8, 16, 33, 64)):
-    rng = np.random.default_rng(20261020)
     out = []
-    for n in sizes:
-        out.append(("uniform%d" % n, rng.uniform(0, 1, (n, n))))  # MatrixTest.java:208-221 builds its inputs like this
+    for n in sizes:  # seeded per size: a subset of sizes gives the same matrices
+        out.append(("uniform%d" % n, np.random.default_rng(20261020 + n).uniform(0, 1, (n, n))))  # MatrixTest.java:208-221
     rng = np.random.default_rng(20261021)  # the special matrices do not depend on `sizes`
     out.append(("zeros1", np.zeros((1, 1))))  # the one all-zero matrix the reference's hqr2 returns from
     out.append(("eye5", np.eye(5)))

@@ -11,6 +11,11 @@ struct HostCta {
     int tid, nthreads;
     pthread_barrier_t *barrier;
     void sync() { pthread_barrier_wait(barrier); }
+    void atomic_max(int *p, int v) {
+        int cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+        while (cur < v && !__atomic_compare_exchange_n(p, &cur, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+        }
+    }
 };
 
 inline void run_cta(int nthreads, const std::function<void(HostCta &)> &body) {

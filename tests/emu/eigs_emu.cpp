@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- drives shared_b200/csrc/eigs_core.cuh (the very code array_eigs.cu launches) on host
-// threads. Usage: eigs_emu <n> <nthreads> <in.f64> <out.f64>; in = n*n doubles, out = n*n (vec) + 2n (val) doubles.
+// threads. Usage: eigs_emu <n> <nthreads> <in.f64> <out.f64> [log_cap chunk_cap]; in = n*n doubles, out = n*n (vec) +
+// 2n (val) doubles. Small log_cap / chunk_cap values exercise the log-full path and the chunked staging.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -10,7 +11,7 @@
 #include "cta_emu.h"
 
 int main(int argc, char **argv) {
-    if (argc != 5) {
+    if (argc != 5 && argc != 7) {
         return 2;
     }
     const int n = atoi(argv[1]), nthreads = atoi(argv[2]);
@@ -25,21 +26,41 @@ int main(int argc, char **argv) {
     std::vector<double> H((size_t) n * ld), V((size_t) n * n), ort((size_t) n + 1), T((size_t) n * n), X((size_t) n * n, 0.0);
     sstc::EigsShared sh;
     memset(&sh, 0, sizeof(sh));
+    const int log_cap = argc == 7 ? atoi(argv[5]) : 8 * n * n + 16, chunk_cap = argc == 7 ? atoi(argv[6]) : 256;
+    std::vector<sstc::EigsRot> log((size_t) log_cap), chunk((size_t) chunk_cap);
+    std::vector<double> Vs((size_t) n * ld);
     double norm = 0.0;
+    int pending = 0;
     run_cta(nthreads, [&](HostCta &cta) {
+        // the sequence of eigs_schur_kernel (array_eigs.cu)
         for (int e = cta.tid; e < n * n; e += cta.nthreads) {
             H[(size_t) (e / n) * ld + e % n] = src[(size_t) e];
         }
         cta.sync();
         sstc::eigs_hessenberg(cta, H.data(), ld, V.data(), ort.data(), n, &sh);
         cta.sync();
-        sstc::eigs_schur(cta, H.data(), ld, V.data(), val.data(), n, &sh, &norm);
+        const int p = sstc::eigs_schur(cta, H.data(), ld, V.data(), val.data(), n, &sh, &norm, log.data(), log_cap,
+                chunk.data(), chunk_cap);
         cta.sync();
+        if (cta.tid == 0) {
+            pending = p;
+        }
         for (int e = cta.tid; e < n * n; e += cta.nthreads) {
             T[(size_t) e] = H[(size_t) (e / n) * ld + e % n];
         }
+        cta.sync();
+        if (p > 0) {  // V takes H's place (padded rows), the log is applied, V goes back
+            for (int e = cta.tid; e < n * n; e += cta.nthreads) {
+                Vs[(size_t) (e / n) * ld + e % n] = V[(size_t) e];
+            }
+            cta.sync();
+            sstc::eigs_apply_rots(cta, Vs.data(), ld, n, log.data(), p, chunk.data(), chunk_cap);
+            for (int e = cta.tid; e < n * n; e += cta.nthreads) {
+                V[(size_t) e] = Vs[(size_t) (e / n) * ld + e % n];
+            }
+        }
     });
-    if (sh.mode == sstc::EIGS_FAILED) {
+    if (pending < 0) {
         return 9;  // "Eigenvalue iteration did not converge"
     }
     if (norm == 0.0) {

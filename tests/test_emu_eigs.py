@@ -30,11 +30,13 @@ def emu():
     return {"fast": fast, "tsan": tsan if os.path.exists(tsan) else None}
 
 
-def run(exe, a, nthreads, tmp_path):
+def run(exe, a, nthreads, tmp_path, caps=()):
+    """caps = (log_cap, chunk_cap): small values force the log-full path and the chunked staging of the rotation log."""
     n = a.shape[0]
     fin, fout = str(tmp_path / "in.f64"), str(tmp_path / "out.f64")
     a.tofile(fin)
-    res = subprocess.run([exe, str(n), str(nthreads), fin, fout], capture_output=True, text=True, timeout=300)
+    res = subprocess.run([exe, str(n), str(nthreads), fin, fout] + [str(c) for c in caps], capture_output=True, text=True,
+                         timeout=300)
     out = np.fromfile(fout) if res.returncode == 0 else np.zeros(n * n + 2 * n)
     return res, out[:n * n], out[n * n:]
 
@@ -58,10 +60,21 @@ def test_emulation_has_no_data_race(emu, tmp_path):
     if emu["tsan"] is None:
         pytest.skip("ThreadSanitizer runtime not installed")
     for name, a in cases(sizes=(1, 2, 3, 5, 8, 16, 33)):
-        res, vec, val = run(emu["tsan"], a, 6, tmp_path)
-        assert "ThreadSanitizer" not in res.stderr, (name, res.stderr[:3000])
-        assert res.returncode == 0, name
-        assert same_bits(vec, GOLDEN[name + "/vec"]) and same_bits(val, GOLDEN[name + "/val"]), name
+        for caps in ((), (7, 3)):
+            res, vec, val = run(emu["tsan"], a, 6, tmp_path, caps)
+            assert "ThreadSanitizer" not in res.stderr, (name, caps, res.stderr[:3000])
+            assert res.returncode == 0, (name, caps)
+            assert same_bits(vec, GOLDEN[name + "/vec"]) and same_bits(val, GOLDEN[name + "/val"]), (name, caps)
+
+
+def test_rotation_log_overflow_and_chunking(emu, tmp_path):
+    """The QR steps are recorded and applied to V afterwards; a full log is applied on the way. Any capacity must give
+    the same bits."""
+    for name, a in cases(sizes=(16, 64)):
+        for caps in ((1, 1), (5, 2), (64, 64), (1000, 7)):
+            res, vec, val = run(emu["fast"], a, 5, tmp_path, caps)
+            assert res.returncode == 0, (name, caps)
+            assert same_bits(vec, GOLDEN[name + "/vec"]) and same_bits(val, GOLDEN[name + "/val"]), (name, caps)
 
 
 def test_emulation_gives_up_where_the_reference_spins(emu, tmp_path):
