@@ -1,7 +1,7 @@
 """Times the SURVEY.md section-8 f-4 members (eigs, insertSparse, sliceSparse) through the host tier of the C ABI on
 one B200, next to the reference's own native code (oracle/_ref, one host core) on the same inputs. These are
 correctness-first kernels off the hot path; the numbers are for the record, not a target.
-Prints one JSON object. Usage: python tools/bench_linalg_sparse.py"""
+Prints one JSON object. Usage: python tools/bench_linalg_sparse.py [--cpu]   (--cpu: also time the reference and compare bits)"""
 import json
 import sys
 import time
@@ -10,12 +10,14 @@ import numpy as np
 
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
-import oracle  # noqa: E402  (the CPU baseline leg, like bench.py's cpu_baseline)
 from shared_b200.array_kernel import CudaArrayKernel  # noqa: E402
 from sparse_cases import dim_offsets, empty_state, row_major  # noqa: E402
 
 k = CudaArrayKernel(0)
-ref = oracle.ref()
+ref = None
+if "--cpu" in sys.argv:  # the CPU baseline leg (like bench.py's cpu_baseline): the reference's native code beside the GPU
+    import oracle
+    ref = oracle.ref()
 rng = np.random.default_rng(1)
 out = {"eigs": [], "sparse": []}
 
