@@ -95,3 +95,37 @@ def test_emulation_matches_live_reference_at_the_reference_tests_size(emu, tmp_p
         assert res.returncode == 0
         assert same_bits(vec, want_vec) and same_bits(val, want_val), n
         assert residual(a, vec, val) < 1e-8, n
+
+
+@pytest.mark.skipif(oracle.ref() is None, reason="oracle/_ref/libsst_ref.so missing")
+def test_emulation_fuzz_structured_matrices(emu, tmp_path):
+    """Small matrices with exact zeros / ties / integer entries walk the rare branches of hqr2 (zero Householder columns,
+    p == 0, s == 0, NaN-producing 2 x 2 zero blocks). The reference is only called where the emulation converged -- same
+    bits, same path -- because the reference has no iteration limit."""
+    rng = np.random.default_rng(20261024)
+    ref = oracle.ref()
+    compared = 0
+    for _ in range(250):
+        size = int(rng.integers(1, 13))
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            a = rng.integers(-2, 3, (size, size)).astype(np.float64)
+        elif kind == 1:
+            a = rng.uniform(-1, 1, (size, size)) * (rng.random((size, size)) < 0.4)
+        elif kind == 2:
+            a = np.triu(rng.integers(-3, 4, (size, size)).astype(np.float64), -1)
+        elif kind == 3:
+            a = rng.standard_normal((size, size))
+            a = a + a.T
+        else:
+            a = rng.integers(0, 2, (size, size)).astype(np.float64)
+        a = np.ascontiguousarray(a)
+        res, vec, val = run(emu["fast"], a, int(rng.integers(1, 9)), tmp_path)
+        if res.returncode == 9:
+            continue
+        assert res.returncode == 0
+        want_vec, want_val = np.zeros(size * size), np.zeros(2 * size)
+        ref.eigs(a.ravel().copy(), want_vec, want_val, size)
+        assert np.array_equal(vec, want_vec, equal_nan=True) and np.array_equal(val, want_val, equal_nan=True), a
+        compared += 1
+    assert compared >= 200
