@@ -93,3 +93,17 @@ def test_tools_and_entry_points_compile():
     paths += [os.path.join(ROOT, "tools", f) for f in sorted(os.listdir(os.path.join(ROOT, "tools"))) if f.endswith(".py")]
     for p in paths:
         compile(open(p).read(), p, "exec")
+
+
+def test_cmake_tree_matches_the_makefile():
+    """native/CMakeLists.txt and shared_b200/csrc/Makefile build the same library: same sources (a glob over csrc/*.cu in
+    both), and the same set of files compiled without FMA contraction -- bit-exact parity depends on that flag."""
+    cm = open(os.path.join(ROOT, "native", "CMakeLists.txt")).read()
+    mk = open(os.path.join(ROOT, "shared_b200", "csrc", "Makefile")).read()
+    nofma_mk = set(re.search(r"^NOFMA := (.*)$", mk, re.M).group(1).split())
+    block = re.search(r"set_source_files_properties\((.*?)PROPERTIES COMPILE_OPTIONS \"-fmad=false\"\)", cm, re.S).group(1)
+    nofma_cm = set(re.findall(r"/(\w+)\.cu", block))
+    assert nofma_mk == nofma_cm and len(nofma_mk) >= 4
+    assert "100a" in cm and "exports.map" in cm and "jni_glue.cpp" in cm
+    for name in nofma_mk:
+        assert os.path.exists(os.path.join(ROOT, "shared_b200", "csrc", name + ".cu")), name
