@@ -14,12 +14,15 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
+#include <vector>
 
 #define JNIEXPORT
 #define JNICALL
 #define JNI_FALSE 0
 #define JNI_TRUE 1
 #define JNI_OK 0
+#define JNI_ERR (-1)
 #define JNI_ABORT 2
 #define JNI_COMMIT 1
 #define JNI_VERSION_1_4 0x00010004
@@ -69,8 +72,12 @@ typedef _jmethodID *jmethodID;
 struct JNIEnv_ {
     bool pending;
     std::string message;
+    /* what a library's JNI_OnLoad did (tests/jni_harness): Services.registerService(spec, impl) calls by class name,
+     * and the last value stored into a static boolean field (Library.initialized) */
+    std::vector<std::pair<std::string, std::string> > registered;
+    int static_boolean;
 
-    JNIEnv_() : pending(false) {}
+    JNIEnv_() : pending(false), static_boolean(-1) {}
 
     static jobject make(int kind, void *data, jint len, int owned) {
         jobject o = (jobject) malloc(sizeof(_jobject));
@@ -110,9 +117,26 @@ struct JNIEnv_ {
         if (!strcmp(name, "[Ljava/lang/Object;")) {
             return classOf(SHIM_OBJECT_ARRAY);
         }
-        return classOf(SHIM_OTHER);
+        /* any other class: a SHIM_CLASS record of kind SHIM_OTHER that remembers its name */
+        static std::vector<jclass> named;
+        for (size_t i = 0; i < named.size(); i++) {
+            if (!strcmp((const char *) named[i]->data, name)) {
+                return named[i];
+            }
+        }
+        jclass c = make(SHIM_CLASS, strdup(name), SHIM_OTHER, 1);
+        named.push_back(c);
+        return c;
     }
     jclass GetObjectClass(jobject o) { return classOf(o->kind); }
+    jobject NewGlobalRef(jobject o) { return o; }
+    void DeleteGlobalRef(jobject) {}
+    void SetIntArrayRegion(jintArray a, jsize start, jsize n, const jint *buf) {
+        memcpy((jint *) a->data + start, buf, (size_t) n * sizeof(jint));
+    }
+    void SetDoubleArrayRegion(jdoubleArray a, jsize start, jsize n, const jdouble *buf) {
+        memcpy((jdouble *) a->data + start, buf, (size_t) n * sizeof(jdouble));
+    }
     jboolean IsInstanceOf(jobject o, jclass c) { return (o && c && c->kind == SHIM_CLASS && o->kind == c->len); }
 
     void *GetPrimitiveArrayCritical(jarray a, jboolean *isCopy) {
@@ -167,8 +191,17 @@ struct JNIEnv_ {
         return to && to->kind == SHIM_CLASS && to->len == SHIM_OBJECT_ARRAY;
     }
     jobject CallObjectMethod(jobject, jmethodID, ...) { return classOf(SHIM_OTHER); }
-    void CallStaticVoidMethod(jclass, jmethodID, ...) {}
-    void SetStaticBooleanField(jclass, jfieldID, jboolean) {}
+    /* the one static void method native code calls: Services.registerService(Class spec, Class impl) */
+    void CallStaticVoidMethod(jclass, jmethodID method, ...) {
+        va_list ap;
+        va_start(ap, method);
+        jclass a = va_arg(ap, jclass), b = va_arg(ap, jclass);
+        va_end(ap);
+        if (a && b && a->kind == SHIM_CLASS && b->kind == SHIM_CLASS && a->data && b->data) {
+            registered.push_back(std::make_pair(std::string((const char *) a->data), std::string((const char *) b->data)));
+        }
+    }
+    void SetStaticBooleanField(jclass, jfieldID, jboolean v) { static_boolean = v ? 1 : 0; }
     /* the one constructor the sources call: SparseArrayState(values, indices, indirectionOffsets, indirections)
      * (NativeArrayKernel.cpp:107); the four array records are kept so that the driver can read them back */
     jobject NewObject(jclass, jmethodID method, ...) {
@@ -196,7 +229,14 @@ struct JNIEnv_ {
 typedef JNIEnv_ JNIEnv;
 
 struct JavaVM_ {
-    jint GetEnv(void **, jint) { return JNI_OK; }
+    JNIEnv_ *env;
+    JavaVM_() : env(0) {}
+    jint GetEnv(void **penv, jint) {
+        if (penv && env) {
+            *penv = env;
+        }
+        return JNI_OK;
+    }
 };
 typedef JavaVM_ JavaVM;
 
