@@ -107,3 +107,29 @@ def test_cmake_tree_matches_the_makefile():
     assert "100a" in cm and "exports.map" in cm and "jni_glue.cpp" in cm
     for name in nofma_mk:
         assert os.path.exists(os.path.join(ROOT, "shared_b200", "csrc", name + ".cu")), name
+
+
+def test_jni_export_signatures_match_the_java_natives():
+    """Type by type: every `native` method of the Java providers against the parameter list of its JNI export
+    (double[] -> jdoubleArray, int -> jint, generic V / Object -> jobject, ...). A JVM resolves natives by name only, so
+    a drifted parameter list would not fail at link time -- it would read garbage."""
+    java_dir = os.path.join(ROOT, "shared_b200", "java", "org", "sharedx", "cuda")
+    glue = open(os.path.join(ROOT, "shared_b200", "csrc", "jni", "jni_glue.cpp")).read()
+    glue = re.sub(r"\bAK\((\w+)\)", r"Java_org_sharedx_cuda_CudaArrayKernel_\1", glue)
+    jtype = {"double[]": "jdoubleArray", "int[]": "jintArray", "int": "jint", "double": "jdouble", "boolean": "jboolean",
+             "long": "jlong", "void": "void", "V": "jobject", "int...": "jintArray", "Object": "jobject", "SparseArrayState<V>": "jobject"}
+    exports = {}
+    for m in re.finditer(r"JNIEXPORT\s+(\w+)\s+JNICALL\s+Java_org_sharedx_cuda_(\w+?)_(\w+)\(JNIEnv \*\w*,\s*jobject\w*(.*?)\)\s*\{",
+                         glue, re.S):
+        params = [re.sub(r"\s+\w+$", "", q.strip()) for q in m.group(4).split(",") if q.strip()]
+        exports[(m.group(2), m.group(3))] = (m.group(1), params)
+    checked = 0
+    for f in sorted(os.listdir(java_dir)):
+        src = re.sub(r"/\*.*?\*/|//[^\n]*", "", open(os.path.join(java_dir, f)).read(), flags=re.S)
+        for m in re.finditer(r"\bnative\s+(?:<V>\s+)?([\w\[\]<>]+)\s+(\w+)\s*\((.*?)\)\s*;", src, re.S):
+            ret, name, plist = m.group(1), m.group(2), m.group(3)
+            params = [jtype[re.sub(r"\s+\w+$", "", q.strip())] for q in plist.split(",") if q.strip()]
+            want = (jtype[ret], params)
+            assert exports.get((f[:-5], name)) == want, (f, name, exports.get((f[:-5], name)), want)
+            checked += 1
+    assert checked >= 25
