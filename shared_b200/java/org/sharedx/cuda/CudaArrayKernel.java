@@ -8,125 +8,129 @@
  * ArrayBase.opKernel.useRegisteredKernel();
  * </pre>
  *
- * The sixteen operations on the FFT / array-kernel hot path are native (JNI glue:
- * shared_b200/csrc/jni/jni_glue.cpp, one export per method, same signatures as NativeArrayKernel.java:56-154).
- * The interface members outside that path (invert, svd, eigs, find, insertSparse, sliceSparse) are native as well:
- * every member of the SPI runs on the GPU, and this provider has no CPU fallback.
+ * Every member of the SPI is a native method served by libsst_cuda.so: the JNI glue
+ * (shared_b200/csrc/jni/jni_glue.cpp) has one export per method, each of which pins the arrays, calls ONE host-tier
+ * function of the C ABI (include/sst_cuda.h, named in the comment of each method below), releases and rethrows the
+ * library's error text as a {@link RuntimeException}. All arithmetic runs on the GPU; there is no CPU fallback.
+ * The parameter lists are those of the interface (ArrayKernel.java:285-674).
  */
 package org.sharedx.cuda;
 
 import org.shared.array.kernel.ArrayKernel;
 import org.shared.array.sparse.SparseArrayState;
 import org.shared.metaclass.Library;
-import org.shared.util.Control;
 
-public class CudaArrayKernel implements ArrayKernel {
+public final class CudaArrayKernel implements ArrayKernel {
 
     /**
-     * Default constructor. Checks the validity of native bindings.
+     * Public and without arguments because {@code Services.createService} instantiates providers reflectively
+     * (Services.java:72-119). Refuses to exist unless libsst_cuda's {@code JNI_OnLoad} found a CUDA device and registered
+     * the providers ({@code Library.initialized}, set by the glue like Library.cpp:77 does).
      */
     public CudaArrayKernel() {
-        Control.checkTrue(Library.isInitialized(), //
-                "Could not instantiate native bindings -- Linking failed");
+        if (!Library.isInitialized()) {
+            throw new RuntimeException("libsst_cuda is not loaded or found no sm_100 device: "
+                    + "the CUDA ArrayKernel cannot be instantiated (there is no CPU fallback)");
+        }
     }
 
-    @Override
-    final public native void randomize();
+    // ---- generator state: sstc_srand --------------------------------------------------------------------------------
 
     @Override
-    final public native void derandomize();
+    public native void randomize();
 
     @Override
-    final public native void map(int[] bounds, //
-            Object srcV, int[] srcD, int[] srcS, //
-            Object dstV, int[] dstD, int[] dstS);
+    public native void derandomize();
+
+    // ---- data movement: sstc_map / sstc_slice (Object[] arrays are moved by the glue on the JVM side) ------------------
 
     @Override
-    final public native void slice(int[] slices, //
-            Object srcV, int[] srcD, int[] srcS, //
-            Object dstV, int[] dstD, int[] dstS);
+    public native void map(int[] bounds, Object srcV, int[] srcD, int[] srcS, Object dstV, int[] dstD, int[] dstS);
 
     @Override
-    final public native void rrOp(int type, //
-            double[] srcV, int[] srcD, int[] srcS, //
-            double[] dstV, int[] dstD, int[] dstS, //
+    public native void slice(int[] slices, Object srcV, int[] srcD, int[] srcS, Object dstV, int[] dstD, int[] dstS);
+
+    // ---- along dimensions: sstc_rrop (reduce), sstc_riop (positions / sort), sstc_rdop (inclusive scan) ----------------
+
+    @Override
+    public native void rrOp(int type, double[] srcV, int[] srcD, int[] srcS, double[] dstV, int[] dstD, int[] dstS,
             int... opDims);
 
     @Override
-    final public native void riOp(int type, //
-            double[] srcV, int[] srcD, int[] srcS, int[] dstV, int dim);
+    public native void riOp(int type, double[] srcV, int[] srcD, int[] srcS, int[] dstV, int dim);
 
     @Override
-    final public native void rdOp(int type, //
-            double[] srcV, int[] srcD, int[] srcS, double[] dstV, //
-            int... opDims);
+    public native void rdOp(int type, double[] srcV, int[] srcD, int[] srcS, double[] dstV, int... opDims);
+
+    // ---- whole-array folds: sstc_raop -> double, sstc_caop -> {re, im} ---------------------------------------------------
 
     @Override
-    final public native double raOp(int type, double[] srcV);
+    public native double raOp(int type, double[] srcV);
 
     @Override
-    final public native double[] caOp(int type, double[] srcV);
+    public native double[] caOp(int type, double[] srcV);
+
+    // ---- element-wise, in place: sstc_ruop / sstc_cuop / sstc_iuop -------------------------------------------------------
 
     @Override
-    final public native void ruOp(int type, double a, double[] srcV);
+    public native void ruOp(int type, double a, double[] srcV);
 
     @Override
-    final public native void cuOp(int type, double aRe, double aIm, double[] srcV);
+    public native void cuOp(int type, double aRe, double aIm, double[] srcV);
 
     @Override
-    final public native void iuOp(int type, int a, int[] srcV);
+    public native void iuOp(int type, int a, int[] srcV);
+
+    // ---- element-wise, binary and conversions: sstc_eop / sstc_convert (runtime type dispatch in the glue) -----------------
 
     @Override
-    final public native void eOp(int type, Object lhsV, Object rhsV, Object dstV, boolean complex);
+    public native void eOp(int type, Object lhsV, Object rhsV, Object dstV, boolean complex);
 
     @Override
-    final public native void convert(int type, //
-            Object srcV, boolean isSrcComplex, //
-            Object dstV, boolean isDstComplex);
+    public native void convert(int type, Object srcV, boolean isSrcComplex, Object dstV, boolean isDstComplex);
+
+    // ---- matrices: sstc_mul (FP64 tensor-pipe GEMM), sstc_diag -----------------------------------------------------------
 
     @Override
-    final public native void mul(double[] lhsV, double[] rhsV, int lr, int rc, double[] dstV, boolean complex);
+    public native void mul(double[] lhsV, double[] rhsV, int lr, int rc, double[] dstV, boolean complex);
 
     @Override
-    final public native void diag(double[] srcV, double[] dstV, int size, boolean complex);
+    public native void diag(double[] srcV, double[] dstV, int size, boolean complex);
 
-    //
+    // ---- decompositions --------------------------------------------------------------------------------------------------
 
-    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_svd -> sstc_svd (one-sided Jacobi on the GPU). */
+    /** sstc_svd: one-sided Jacobi on the GPU; singular vectors agree with JAMA's up to the sign of each pair. */
     @Override
-    final public native void svd(double[] srcV, int srcStrideRow, int srcStrideCol, //
-            double[] uV, double[] sV, double[] vV, int nRows, int nCols);
+    public native void svd(double[] srcV, int srcStrideRow, int srcStrideCol, double[] uV, double[] sV, double[] vV,
+            int nRows, int nCols);
 
     /**
-     * JNI: Java_org_sharedx_cuda_CudaArrayKernel_eigs -> sstc_eigs (Hessenberg + double-shift QR in one CTA,
-     * back-substitution with one thread per eigenvalue; bit-identical to the reference's native kernel).
+     * sstc_eigs: Hessenberg reduction + double-shift QR in one CTA, back-substitution with one thread per eigenvalue;
+     * bit-identical to the reference's native kernel.
      */
     @Override
-    final public native void eigs(double[] srcV, double[] vecV, double[] valV, int size);
+    public native void eigs(double[] srcV, double[] vecV, double[] valV, int size);
 
-    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_invert -> sstc_invert (LU with partial pivoting on the GPU). */
+    /** sstc_invert: LU with partial pivoting (JAMA's pivot rule) and the two triangular solves on the GPU. */
     @Override
-    final public native void invert(double[] srcV, double[] dstV, int size);
+    public native void invert(double[] srcV, double[] dstV, int size);
 
-    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_find -> sstc_find; the result array is allocated by the glue. */
+    // ---- index extraction and sparse arrays ------------------------------------------------------------------------------
+
+    /** sstc_find; the {@code int[]} result is allocated by the glue. */
     @Override
-    final public native int[] find(int[] srcV, int[] srcD, int[] srcS, int[] logical);
+    public native int[] find(int[] srcV, int[] srcD, int[] srcS, int[] logical);
 
     /**
-     * JNI: Java_org_sharedx_cuda_CudaArrayKernel_insertSparse -> sstc_insert_sparse (pair sort, scan-ranked merge and
-     * per-dimension metadata on the GPU); the SparseArrayState is constructed by the glue. Object[] values are gathered
-     * on the JVM side from the positions the device computes.
+     * sstc_insert_sparse: pair sort, scan-ranked merge and per-dimension metadata on the GPU. The glue constructs the
+     * {@link SparseArrayState}; {@code Object[]} values are gathered on the JVM side from positions the device computes.
      */
     @Override
-    final public native <V> SparseArrayState<V> insertSparse( //
-            V oldV, int[] oldD, int[] oldS, int[] oldDo, int[] oldI, //
-            V newV, int[] newI);
+    public native <V> SparseArrayState<V> insertSparse(V oldV, int[] oldD, int[] oldS, int[] oldDo, int[] oldI, V newV,
+            int[] newI);
 
-    /** JNI: Java_org_sharedx_cuda_CudaArrayKernel_sliceSparse -> sstc_slice_sparse. */
+    /** sstc_slice_sparse. */
     @Override
-    final public native <V> SparseArrayState<V> sliceSparse(int[] slices, //
-            V srcV, int[] srcD, int[] srcS, int[] srcDo, //
-            int[] srcI, int[] srcIo, int[] srcIi, //
-            V dstV, int[] dstD, int[] dstS, int[] dstDo, //
-            int[] dstI, int[] dstIo, int[] dstIi);
+    public native <V> SparseArrayState<V> sliceSparse(int[] slices, V srcV, int[] srcD, int[] srcS, int[] srcDo, int[] srcI,
+            int[] srcIo, int[] srcIi, V dstV, int[] dstD, int[] dstS, int[] dstDo, int[] dstI, int[] dstIo, int[] dstIi);
 }

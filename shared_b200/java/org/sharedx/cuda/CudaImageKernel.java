@@ -17,28 +17,26 @@ package org.sharedx.cuda;
 
 import org.shared.image.kernel.ImageKernel;
 import org.shared.metaclass.Library;
-import org.shared.util.Control;
 
-public class CudaImageKernel implements ImageKernel {
+public final class CudaImageKernel implements ImageKernel {
 
     /**
-     * Default constructor (instantiated reflectively by {@code Services.createService}); same linking check as
-     * {@code NativeImageKernel} (NativeImageKernel.java:45-49).
+     * Public and without arguments: {@code Services.createService} instantiates providers reflectively. Refuses to exist
+     * unless libsst_cuda's {@code JNI_OnLoad} found a CUDA device and registered the providers.
      */
     public CudaImageKernel() {
-        Control.checkTrue(Library.isInitialized(), //
-                "Could not instantiate native bindings -- Linking failed");
+        if (!Library.isInitialized()) {
+            throw new RuntimeException("libsst_cuda is not loaded or found no sm_100 device: "
+                    + "the CUDA ImageKernel cannot be instantiated (there is no CPU fallback)");
+        }
     }
 
-    /** JNI: Java_org_sharedx_cuda_CudaImageKernel_createIntegralImage -> sstc_integral_image. */
+    /** sstc_integral_image (JNI export Java_org_sharedx_cuda_CudaImageKernel_createIntegralImage). */
     @Override
-    final public native void createIntegralImage( //
-            double[] srcV, int[] srcD, int[] srcS, //
-            double[] dstV, int[] dstD, int[] dstS);
+    public native void createIntegralImage(double[] srcV, int[] srcD, int[] srcS, double[] dstV, int[] dstD, int[] dstS);
 
-    /** JNI: Java_org_sharedx_cuda_CudaImageKernel_createIntegralHistogram -> sstc_integral_histogram. */
+    /** sstc_integral_histogram (JNI export Java_org_sharedx_cuda_CudaImageKernel_createIntegralHistogram). */
     @Override
-    final public native void createIntegralHistogram( //
-            double[] srcV, int[] srcD, int[] srcS, int[] memV, //
-            double[] dstV, int[] dstD, int[] dstS);
+    public native void createIntegralHistogram(double[] srcV, int[] srcD, int[] srcS, int[] memV, double[] dstV, int[] dstD,
+            int[] dstS);
 }
