@@ -15,7 +15,6 @@ package org.sharedx.cuda;
 
 import org.shared.fft.FftService;
 import org.shared.metaclass.Library;
-import org.shared.util.Control;
 
 public class CudaFftService implements FftService {
 
@@ -29,12 +28,15 @@ public class CudaFftService implements FftService {
     volatile String mode = "estimate";
 
     /**
-     * Default constructor (instantiated reflectively by {@code Services.createService}). Checks the validity
-     * of the native bindings exactly like {@code NativeArrayKernel} does (NativeArrayKernel.java:46-49).
+     * Public and without arguments: {@code Services.createService} instantiates providers reflectively. Refuses to exist
+     * unless libsst_cuda's {@code JNI_OnLoad} found a CUDA device and registered the providers (the same gate the
+     * reference's native providers have, NativeArrayKernel.java:46-49).
      */
     public CudaFftService() {
-        Control.checkTrue(Library.isInitialized(), //
-                "Could not instantiate native bindings -- Linking failed");
+        if (!Library.isInitialized()) {
+            throw new RuntimeException("libsst_cuda is not loaded or found no sm_100 device: "
+                    + "the CUDA FftService cannot be instantiated (there is no CPU fallback)");
+        }
     }
 
     /** JNI: Java_org_sharedx_cuda_CudaFftService_transform -> sstc_fft. */
