@@ -133,3 +133,56 @@ def test_jni_export_signatures_match_the_java_natives():
             assert exports.get((f[:-5], name)) == want, (f, name, exports.get((f[:-5], name)), want)
             checked += 1
     assert checked >= 25
+
+
+def test_sparse_argument_checks_need_no_device():
+    """The reference validates before it touches array contents (SparseOpsInsert.cpp:77-108, SparseOpsSlice.cpp:87-166);
+    so does the C ABI: these calls fail with the reference's texts before any CUDA call, hence also on a box without a GPU."""
+    import ctypes
+
+    import numpy as np
+
+    from shared_b200 import _lib
+    from shared_b200.array_kernel import SparseStateStruct
+    lib = _lib.lib()
+
+    def i32(v):
+        return np.ascontiguousarray(v, dtype=np.int32)
+
+    def pi(a):
+        return a.ctypes.data_as(_lib.c_i32_p)
+
+    def vp(a):
+        return ctypes.c_void_p(a.ctypes.data)
+
+    st = SparseStateStruct()
+    vals, idx = np.array([1.0, 2.0]), i32([1, 3])
+    empty_v, empty_i = np.zeros(1), i32([0])
+
+    def insert(D, S, Do, elem_bytes=8):
+        D, S, Do = i32(D), i32(S), i32(Do)
+        return lib.sstc_insert_sparse(elem_bytes, vp(empty_v), 0, pi(D), pi(S), pi(Do), D.size, vp(empty_i), vp(vals), 2,
+                                      vp(idx), ctypes.byref(st))
+
+    def last():
+        return lib.sstc_last_error().decode()
+
+    assert insert([2, 3], [4, 1], [0, 3, 7]) == 1 and last() == "Invalid dimensions and/or strides"
+    assert insert([2, -3], [3, 1], [0, 3, 7]) == 1 and last() == "Invalid dimensions and/or strides"
+    assert insert([2, 3], [3, 1], [0, 3, 8]) == 1 and last() == "Invalid arguments"
+    assert insert([2, 3], [3, 1], [0, 3, 7], elem_bytes=2) == 1 and last() == "Invalid array types"
+    assert lib.sstc_insert_sparse(8, vp(empty_v), 0, pi(i32([2])), pi(i32([1])), pi(i32([0, 3])), 1, vp(empty_i), vp(vals), 2,
+                                  vp(idx), None) == 1 and last() == "Invalid arguments"
+
+    D, S, Do = i32([2, 3]), i32([3, 1]), i32([0, 3, 7])
+    io, ii = i32(np.zeros(7)), i32([0])
+
+    def slc(slices):
+        sl = i32(slices)
+        return lib.sstc_slice_sparse(8, pi(sl), sl.size, vp(empty_v), 0, pi(D), pi(S), pi(Do), vp(empty_i), pi(io), vp(ii),
+                                     vp(empty_v), 0, pi(D), pi(S), pi(Do), vp(empty_i), pi(io), vp(ii), 2, ctypes.byref(st))
+
+    assert slc([0, 0, 2]) == 1 and last() == "Invalid dimension"
+    assert slc([2, 0, 0]) == 1 and last() == "Invalid index"
+    assert slc([0, 3, 1]) == 1 and last() == "Invalid index"
+    assert slc([0, 0]) == 1 and last() == "Invalid arguments"
