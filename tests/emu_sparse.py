@@ -20,7 +20,7 @@ def build():
     """-> (build dir, make's output); raises RuntimeError when the tool chain is missing."""
     if shutil.which("g++") is None or shutil.which("make") is None:
         raise RuntimeError("no g++ / make")
-    res = subprocess.run(["make", "-s", "-C", EMU_DIR, "all"], capture_output=True, text=True)
+    res = subprocess.run(["make", "-s", "-k", "-C", EMU_DIR, "all"], capture_output=True, text=True)
     return os.path.join(EMU_DIR, "_build"), res.stdout[-2000:] + res.stderr[-2000:]
 
 

@@ -22,7 +22,7 @@ GOLDEN = np.load(os.path.join(HERE, "golden", "eigs_golden.npz"))
 def emu():
     if shutil.which("g++") is None or shutil.which("make") is None:
         pytest.skip("no g++ / make")
-    res = subprocess.run(["make", "-s", "-C", EMU, "all"], capture_output=True, text=True)
+    res = subprocess.run(["make", "-s", "-k", "-C", EMU, "all"], capture_output=True, text=True)
     fast = os.path.join(EMU, "_build", "eigs_emu_fast")
     tsan = os.path.join(EMU, "_build", "eigs_emu_tsan")
     if not os.path.exists(fast):

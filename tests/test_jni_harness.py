@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def jh():
     if shutil.which("g++") is None or shutil.which("make") is None:
         pytest.skip("no g++ / make")
-    res = subprocess.run(["make", "-s", "-C", os.path.join(HERE, "jni_harness"), "all"], capture_output=True, text=True)
+    res = subprocess.run(["make", "-s", "-k", "-C", os.path.join(HERE, "jni_harness"), "all"], capture_output=True, text=True)
     path = os.path.join(HERE, "jni_harness", "_build", "libjni_harness.so")
     if not os.path.exists(path):
         pytest.fail("harness build failed:\n" + res.stdout[-3000:] + res.stderr[-3000:])
