@@ -3,127 +3,45 @@ fftShift) replayed through shared_b200.proto_array.ProtoArray -- the host-side m
 ArrayKernel.map / slice -- with the reference's own native kernel as the provider. What is pinned here, on a box without
 a GPU, is the bounds / slices arithmetic of tile, transpose, shift, subarray, reverse, concat, reverseOrder and the slice
 variants against the literal known-answer arrays of the reference's tests (all `Arrays.equals`: exact). The same class
-over CudaArrayKernel issues the same kernel calls."""
+over CudaArrayKernel issues the same kernel calls (checks shared through tests/proto_array_checks.py)."""
 import numpy as np
 import pytest
 
 import oracle
-from conftest import golden
-from shared_b200.proto_array import FAR, NEAR, ProtoArray
+import proto_array_checks as pc
 
 ref = oracle.ref()
 pytestmark = pytest.mark.skipif(ref is None, reason="oracle/_ref/libsst_ref.so missing")
 
 
-def arr(rec, dtype=np.float64):
-    return ProtoArray(ref, np.array(rec["values"], dtype=dtype), rec["dims"], rec["order"] or FAR)
-
-
-def same(a, rec):
-    return np.array_equal(a.values, np.array(rec["values"], dtype=a.values.dtype))
-
-
 @pytest.mark.parametrize("fixture,dtype", [("RealArrayTest", np.float64), ("IntegerArrayTest", np.int32)])
 def test_map(fixture, dtype):
-    a = arr(golden(fixture)["testMap"][0], dtype)  # RealArrayTest.java:64-93, IntegerArrayTest.java:58-86
-    bounds = (1, 0, 2, 0, 1, 2, 1, 0, 3)
-    expected = a.map(ProtoArray(ref, None, [3, 3, 4], NEAR, dtype=dtype), *bounds)
-    got = a.map(ProtoArray(ref, None, [3, 3, 4], FAR, dtype=dtype), *bounds)
-    assert np.array_equal(got.reverseOrder().values, expected.values) and got.values.any()
+    pc.check_map(ref, fixture, dtype)
 
 
 def test_slice_variants():
-    r = golden("RealArrayTest")["testSlice"]  # RealArrayTest.java:100-229
-    original = arr(r[0])
-    a = original.splice(ProtoArray(ref, None, [5, 5]), 1, 0, 0, 3, 2, 0, 5, 4, 0, 0, 0, 1, 2, 1, 1, 4, 3, 1, 6, 4, 1)
-    assert same(a, r[1])
-    a = original.slice_into([r[2]["values"], r[3]["values"]], ProtoArray(ref, None, [5, 5]), [r[4]["values"], r[5]["values"]])
-    assert same(a, r[1])
-    a = arr(r[6]).slice_to(ProtoArray(ref, None, [5, 5]), r[8]["values"], r[9]["values"])
-    assert same(a, r[7])
-    a = arr(r[10]).slice_fill(0.0, r[12]["values"], r[13]["values"])
-    assert same(a, r[11])
-    a = original.slice(r[14]["values"], r[15]["values"])
-    assert a.dims == [3, 4] and same(a, r[16])
+    pc.check_slice_variants(ref)
 
 
 def test_integer_slice():
-    r = golden("IntegerArrayTest")["testSlice"]  # IntegerArrayTest.java:94-178
-    a = arr(r[0], np.int32).splice(ProtoArray(ref, None, [2, 3, 4], NEAR, dtype=np.int32),
-                                   1, 0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 1, 1, 0, 2, 2, 1, 2, 2, 2, 2, 3, 3, 2)
-    assert same(a.reverseOrder(), r[1])
-    a = arr(r[2], np.int32).splice(ProtoArray(ref, None, [3, 3], dtype=np.int32), 1, 0, 0, 2, 1, 0, 3, 2, 0, 0, 0, 1, 2, 1, 1,
-                                   4, 2, 1)
-    assert same(a, r[3])
+    pc.check_integer_slice(ref)
 
 
 def test_tile_transpose_shift_subarray():
-    r = golden("RealArrayTest")
-    t = r["testTile"]  # RealArrayTest.java:238-300
-    assert same(arr(t[0]).tile(2, 2, 2), t[1]) and same(arr(t[2]).tile(1, 5), t[3])
-    t = r["testTranspose"]  # :309-372
-    assert same(arr(t[0]).transpose(1, 0), t[1])
-    got = arr(t[2]).transpose(2, 0, 1)
-    assert got.dims == [4, 5, 3] and same(got, t[3])
-    t = r["testShift"]  # :390-443
-    assert same(arr(t[0]).shift(-3, -1, 1), t[1])
-    t = r["testSubarray"]  # :471-506
-    got = arr(t[0]).subarray(1, 3, 1, 4, 1, 3)
-    assert got.dims == [2, 3, 2] and same(got, t[1])
+    pc.check_tile_transpose_shift_subarray(ref)
 
 
 def test_reshape_reverse_concat_reverse_order():
-    r = golden("RealArrayTest")
-    t = r["testReshape"]  # RealArrayTest.java:520-575
-    a = arr(t[0])
-    assert same(a.mMul(a.reshape(6, 3)), t[1])
-    assert same(arr(t[2]).reshape(9, 3).tile(1, 2), t[3])
-    t = r["testReverse"]  # :587-630
-    assert same(arr(t[0]).reverse(2, 0), t[1])
-    t = r["testConcat"]  # :638-682
-    a, b = arr(t[0]), arr(t[1])
-    got = a.concat(1, b, a)
-    assert got.dims == [2, 7, 2] and same(got, t[2])
-    t = r["testReverseOrder"]  # :695-720
-    got = arr(t[0]).reverseOrder().reverseOrder().reverseOrder()
-    assert got.order == NEAR and same(got, t[1])
+    pc.check_reshape_reverse_concat_reverse_order(ref)
 
 
 def test_fft_shift_is_a_shift_of_the_complex_array(fft_kats):
-    """AbstractComplexArray.fftShift (AbstractComplexArray.java:85-97): shift by dims / 2 over every dimension but the
-    trailing re / im pair. ArrayFftTest.java:232-284."""
-    recs = fft_kats["testFftShift"]
-    a = arr(recs[0])
-    assert a.dims[-1] == 2
-    shifts = [d // 2 for d in a.dims[:-1]] + [0]
-    assert same(a.shift(*shifts), recs[1])
-    back = [-(d // 2) for d in a.dims[:-1]] + [0]
-    assert np.array_equal(a.shift(*shifts).shift(*back).values, a.values)
+    pc.check_fft_shift_is_a_shift_of_the_complex_array(ref, fft_kats)
 
 
 def test_integer_find():
-    """IntegerArray.find (IntegerArray.java) -> ArrayKernel.find on the positions riOp wrote. IntegerArrayTest.java:185-217."""
-    r = golden("IntegerArrayTest")["testFind"]
-    a = arr(r[0], np.int32)
-    k = 1
-    for i in range(3):
-        for j in range(4):
-            got = ref.find(a.values, a.dims, a.strides, [i, j, -1])
-            assert np.array_equal(got, np.array(r[k]["values"], dtype=np.int32)), (i, j)
-            k += 1
+    pc.check_integer_find(ref)
 
 
 def test_argument_errors():
-    a = ProtoArray(ref, np.arange(6.0), [2, 3])
-    with pytest.raises(ValueError, match="Invalid permutation"):
-        a.transpose(1, 1)
-    with pytest.raises(ValueError, match="Dimensionality mismatch"):
-        a.tile(2)
-    with pytest.raises(ValueError, match="Invalid subarray bounds"):
-        a.subarray(0, 1)
-    with pytest.raises(ValueError, match="Cardinality mismatch"):
-        a.reshape(4, 2)
-    with pytest.raises(ValueError, match="Source and destination cannot be the same"):
-        a.map(a, 0, 0, 2, 0, 0, 3)
-    with pytest.raises(ValueError, match="Dimension mismatch"):
-        a.concat(0, ProtoArray(ref, np.arange(4.0), [2, 2]))
+    pc.check_argument_errors(ref)
