@@ -107,6 +107,18 @@ class ClockSampler:
 # reference arm / cpu baseline: the CPU oracle (single-threaded, like every provider of the reference)
 # --------------------------------------------------------------------------------------------------------
 
+def cpu_model():
+    """Model name of the host CPU the baseline ran on (SURVEY.md 8d asks for it next to the core count)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_fft_seconds(dims, reps):
     import numpy as np
     import oracle
@@ -127,7 +139,7 @@ def cpu_baseline(sample=(256, 256, 256)):
     secs = cpu_fft_seconds(sample, 1)
     n = sample[0] * sample[1] * sample[2]
     return {"value": fft_flops(n) / secs / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-            "host_cores": os.cpu_count(), "seconds": secs,
+            "host_cores": os.cpu_count(), "cpu_model": cpu_model(), "seconds": secs,
             "sample": "forward c2c %dx%dx%d (1/%d of the 512^3 points), oracle/fftops_oracle.c = C restatement of "
                       "FftOps.java, gcc -O2, 1 thread (the reference path is single-threaded)" %
                       (sample + ((DIMS[0] * DIMS[1] * DIMS[2]) // n,))}
@@ -158,7 +170,7 @@ def run_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward)", "sample": desc},
         "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": desc,
-                         "host_cores": os.cpu_count()},
+                         "host_cores": os.cpu_count(), "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
