@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SSTC_ABI_VERSION 1
+#define SSTC_ABI_VERSION 2
 
 /* ---- library / device ------------------------------------------------------------------------------- */
 
@@ -65,9 +65,22 @@ int sstc_fft_lengths(int kind, int rank, const int32_t *dims, int64_t *in_len, i
 
 /* HOST tier. Replaces Java_org_sharedx_fftw_Plan_transform (native/src/sharedx/BindingsX.cpp:26-29,
  * Plan.cpp:44-99) and JavaFftService.{fft,ifft,rfft,rifft} (src/org/shared/fft/JavaFftService.java:53-94).
- * `in` is preserved. Length mismatch fails with "Input and/or output arrays do not have expected sizes". */
+ * `in` is preserved. Length mismatch fails with "Input and/or output arrays do not have expected sizes".
+ * Re-entrant: concurrent callers run on separate slots (streams, buffers) and share the two PCIe directions. The
+ * arrays may be pageable (a JVM heap array under GetPrimitiveArrayCritical) or pinned; pageable ones are staged through
+ * a pinned ring by copy threads, pipelined with the DMA. The input is transferred in chunks of planes of dims[0] and
+ * every inner axis is transformed behind the copy; dims[0] is transformed in column groups in front of the D2H copy. */
 int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t in_len, double *out,
         int64_t out_len);
+
+/* Tunables of the host tier (process-wide; the FftService.setHint analogue for the transfer side). Names:
+ *   "slots"        transforms that may be in flight at once per device (default 2; each holds its own device buffers,
+ *                  streams and pinned staging ring, so that one caller's D2H overlaps another's H2D);
+ *   "copy_threads" threads that move pageable arrays through the pinned staging ring (default min(8, cores/2));
+ *   "chunk_mib"    staging / pipelining granularity (default 32);
+ *   "pipeline"     0 = H2D, all passes, D2H strictly one after the other (for A/B measurements), 1 = default.
+ * Environment: SSTC_HOST_SLOTS, SSTC_HOST_COPY_THREADS, SSTC_HOST_CHUNK_MIB, SSTC_HOST_PIPELINE. */
+int sstc_host_option(const char *name, int64_t value);
 
 /* DEVICE tier. A plan replaces the fftw_plan held by org.sharedx.fftw.Plan (Plan.cpp:101-141 create,
  * :143-175 destroy); creation is serialised internally, execution is re-entrant per stream. */
@@ -138,6 +151,52 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
 int sstc_fft_planes_scatter_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int32_t block_planes,
         int32_t plane_lines, int32_t dst_plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale,
         int64_t max_ctas, void *stream);
+
+/* ---- slab-decomposed 3-D transform over the GPUs of one box (the reference has no distributed
+ * path, FftService.java:38-106 is what it extends) ------------------------------------------------------------------
+ *
+ * dims (d0, d1, d2) complex128, P ranks, P | d0, P | d1, d2 a power of two in [8, 4096], d0 and d1 <= 4096 (or any length
+ * <= 7168). "Natural" slabs: rank g holds x[g*d0/P : (g+1)*d0/P, :, :]; "transposed" slabs: rank g holds
+ * X[:, g*d1/P : (g+1)*d1/P, :] as a dense (d0, d1/P, d2) array. forward: natural -> transposed, unscaled; inverse:
+ * transposed -> natural, scaled by 1/N. The schedule (y pass locally, z pass storing whole lines into the owners'
+ * buffers over NVLink group by group, flag barrier, x pass of each group beside the rest of the exchange) runs on the
+ * context's own streams, joined to `stream` on both sides, and is replayed from a CUDA graph after two eager calls with
+ * the same input pointer.
+ *
+ * sstc_slab: ONE rank's context, for the one-process-per-GPU layout. d_recv0 / d_recv1 [nranks]: every rank's two receive
+ * buffers (d0*d1*d2/P complex each) as mapped in THIS process (sstc_ipc_open; entry `rank` is this rank's own
+ * allocation); d_flags [nranks]: every rank's zero-initialised flag array (16 uint64). All ranks must issue the same
+ * sequence of forward / inverse calls. *d_out receives this rank's result slab inside its own receive buffer: valid
+ * until the next-but-one call on this context, provided its consumers are enqueued on `stream` before the next call.
+ * A peer that never arrives makes a later call fail with "peer barrier timed out" instead of returning stale data. */
+typedef struct sstc_slab_s *sstc_slab;
+int sstc_slab_create(sstc_slab *slab, const int32_t *dims, int nranks, int rank, void *const *d_recv0, void *const *d_recv1,
+        void *const *d_flags);
+int sstc_slab_forward(sstc_slab slab, const double *d_in, double **d_out, void *stream);
+int sstc_slab_inverse(sstc_slab slab, const double *d_in, double **d_out, void *stream);
+/* Options: "groups" (pipeline groups of the exchange, default 4), "chunks" (the local pass in front of the exchange is
+ * cut into this many pieces and the first group follows piece by piece; default 4 at 8 ranks, else 1), "exchange_ctas"
+ * (grid cap of the exchange pass; default one CTA per SM, two at 2 ranks; 0 = uncapped), "bulk_store" (1: every
+ * transformed line leaves shared memory as one cp.async.bulk copy instead of per-thread stores), "graph" (0: always
+ * issue eagerly). Setting an option drops the recorded graphs. */
+int sstc_slab_set_option(sstc_slab slab, const char *name, int64_t value);
+int64_t sstc_slab_graph_count(sstc_slab slab);
+int sstc_slab_destroy(sstc_slab slab);
+
+/* The same transform driven from ONE process over `ndev` devices (devices == NULL: 0..ndev-1): the library allocates
+ * the receive buffers and flags on every device and enables peer access (cudaDeviceEnablePeerAccess). d_in[r] / d_out[r]
+ * are rank r's slabs on devices[r]; streams[r] (or NULL: the plan's own stream per device) is the stream rank r's work
+ * is joined to. Calls return without synchronising; sstc_fft3d_sharded_sync waits for every device.
+ * sstc_fft3d_sharded_host is the HOST tier: whole (d0, d1, d2) arrays in host memory, natural order in and out; every
+ * device moves its slab over its own PCIe link. This is what CudaFftService.setHint("devices", ...) binds. */
+typedef struct sstc_fft3d_sharded_s *sstc_fft3d_sharded;
+int sstc_fft3d_sharded_create(sstc_fft3d_sharded *plan, const int32_t *dims, int ndev, const int32_t *devices);
+int sstc_fft3d_sharded_forward(sstc_fft3d_sharded plan, const double *const *d_in, double **d_out, void *const *streams);
+int sstc_fft3d_sharded_inverse(sstc_fft3d_sharded plan, const double *const *d_in, double **d_out, void *const *streams);
+int sstc_fft3d_sharded_sync(sstc_fft3d_sharded plan);
+int sstc_fft3d_sharded_set_option(sstc_fft3d_sharded plan, const char *name, int64_t value);
+int sstc_fft3d_sharded_host(sstc_fft3d_sharded plan, int inverse, const double *in, double *out);
+int sstc_fft3d_sharded_destroy(sstc_fft3d_sharded plan);
 
 /* Cross-GPU barrier kernel (one process per GPU): d_flag_arrays[r] is rank r's array of 8 uint64 epoch slots,
  * mapped by every rank (sstc_ipc_*) and zero-initialised (at least 9 slots: slot 8 is the rank's own call

@@ -131,6 +131,7 @@ struct JNIEnv_ {
     jclass GetObjectClass(jobject o) { return classOf(o->kind); }
     jobject NewGlobalRef(jobject o) { return o; }
     void DeleteGlobalRef(jobject) {}
+    void DeleteLocalRef(jobject) {}
     void SetIntArrayRegion(jintArray a, jsize start, jsize n, const jint *buf) {
         memcpy((jint *) a->data + start, buf, (size_t) n * sizeof(jint));
     }

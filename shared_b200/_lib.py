@@ -36,6 +36,7 @@ SIGNATURES = {
     "sstc_fft_lengths": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i32_p, c_i64_p, c_i64_p]),
     "sstc_fft": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i32_p, ctypes.c_void_p, ctypes.c_int64,
                                 ctypes.c_void_p, ctypes.c_int64]),
+    "sstc_host_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "sstc_fft_plan_create": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, c_i32_p]),
     "sstc_fft_plan_execute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sstc_fft_plan_destroy": (ctypes.c_int, [ctypes.c_void_p]),
@@ -58,6 +59,19 @@ SIGNATURES = {
     "sstc_fft_planes_scatter_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
                                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                    ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
+    "sstc_slab_create": (ctypes.c_int, [c_void_pp, c_i32_p, ctypes.c_int, ctypes.c_int, c_void_pp, c_void_pp, c_void_pp]),
+    "sstc_slab_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
+    "sstc_slab_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
+    "sstc_slab_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "sstc_slab_graph_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "sstc_slab_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "sstc_fft3d_sharded_create": (ctypes.c_int, [c_void_pp, c_i32_p, ctypes.c_int, c_i32_p]),
+    "sstc_fft3d_sharded_forward": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "sstc_fft3d_sharded_inverse": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "sstc_fft3d_sharded_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "sstc_fft3d_sharded_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "sstc_fft3d_sharded_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "sstc_fft3d_sharded_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "sstc_peer_barrier_dev": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]),
     "sstc_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "sstc_ipc_open": (ctypes.c_int, [ctypes.c_char_p, c_void_pp]),

@@ -64,6 +64,10 @@ struct FftPassArgs {
     // block and stores line yl of plane xl of block q at blk[q] + (xl*ls_plane_lines + yl)*L (ls_plane_lines = the
     // destination's lines per plane).
     int ls_group, ls_nblk, ls_first, ls_block_lines, ls_plane_lines, ls_sub;
+    // ls_bulk: the transformed line is put back into shared memory and leaves as ONE bulk asynchronous copy
+    // (cp.async.bulk shared::cta -> global, SASS UBLKCP) issued by one thread per line, instead of 16-byte stores from
+    // every thread: the copy engine of the SM streams the 16*L bytes to the peer and the LSU is free for the next tile.
+    int ls_bulk;
     // Fused convolution (EXT kernels and the any-length kernel; all off when mul == nullptr and crop_cols == 0):
     //   mul        every point loaded by a c2c (natural layout) or c2r pass is first multiplied by mul[same index]
     //              -- the eMul of ConvolutionCache.convolve folded into the first inverse pass;
@@ -357,10 +361,29 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
 
     Pow2Stages<L, C, STRIDED, 1>::run(v, t, c, sm, a.tw);
 
+    const double s = a.scale;
+    if (EXT && !STRIDED && L >= 16 && a.ls_group > 0 && a.ls_bulk) {
+        // every thread takes part (barriers), inactive lines just do not issue a copy
+        __syncthreads();  // the last exchange has been read by everyone
+        double2 *ln = sm + c * L;  // dense line (the padded exchange layout is not contiguous)
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            ln[t + m * T] = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+        __syncthreads();
+        if (t == 0 && active) {
+            const uint32_t src = (uint32_t) __cvta_generic_to_shared(ln);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out_line), "r"(src),
+                         "r"((uint32_t) (L * 16))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+    }
     if (!active) {
         return;
     }
-    const double s = a.scale;
     if (EXT && STRIDED && a.ksplit > 0) {
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -425,8 +448,14 @@ fft_pow2_ext_kernel(const FftPassArgs a) {
         // reverse: walk the tiles from the end (the data the previous pass wrote last is still in L2)
         fft_pow2_tile<L, C, STRIDED, true>(a, a.reverse ? a.ntiles - 1 - blk : blk, sm);
         if (blk + gridDim.x < a.ntiles) {
+            if (!STRIDED && a.ls_bulk) {  // the issuing threads: the bulk copies have read their shared-memory source
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
             __syncthreads();
         }
+    }
+    if (!STRIDED && a.ls_bulk) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // writes performed before the CTA retires
     }
 }
 

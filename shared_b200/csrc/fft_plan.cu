@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "fft_aux_kernels.cuh"
+#include "fft_internal.h"
 #include "fft_kernels.cuh"
 #include "sstc_internal.h"
 
@@ -306,7 +307,7 @@ struct Fuse {
     int32_t crop_in[4] = {1, 1, 1, 1}, crop_out[4] = {1, 1, 1, 1};
 };
 
-static bool tile_kernels_hold(int L) {
+bool tile_kernels_hold(int L) {
     const bool is_pow2 = (L & (L - 1)) == 0;
     return is_pow2 ? L <= 4096 : L <= kGenericMaxL;
 }
@@ -352,7 +353,7 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.mode = mode;
     a.inverse = inverse;
     a.ksplit = a.in_ksplit = 0;
-    a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = a.ls_sub = 0;
+    a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = a.ls_sub = a.ls_bulk = 0;
     a.ntiles = a.grid_limit = 0;
     a.reverse = reverse;
     a.mul = fuse ? fuse->mul : nullptr;
@@ -419,7 +420,12 @@ static void dispatch_axis(const FftPassArgs &a, int L, bool strided, cudaStream_
 // Bluestein (chirp-z) over power-of-two transforms of size M >= 2L-1. Both need a workspace of the size of the
 // data they touch, taken from per-thread grow-only scratch.
 
-static thread_local Scratch t_fft_ws[3];  // 0: Bluestein lines, 1: four-step transpose, 2: real<->complex staging
+// 0: Bluestein lines, 1: four-step transpose, 2: real<->complex staging. Per host thread AND per stream: two streams
+// driven by one thread may run their long-axis passes concurrently.
+struct FftWorkspaces {
+    Scratch ws[3];
+};
+static thread_local std::map<cudaStream_t, FftWorkspaces> t_fft_ws;
 static const int kMaxAxisLog2 = 24;
 static std::map<std::vector<int64_t>, double2 *> g_bluestein_filters;  // (device, L, M, inverse) -> FFT_M(b)
 
@@ -439,7 +445,7 @@ static void fourstep_axis(const double2 *in, double2 *out, int64_t outer, int L,
     }
     const int L1 = 1 << ((lg + 1) / 2), L2 = L / L1;
     const int64_t n = outer * (int64_t) L * inner;
-    double2 *tmp = static_cast<double2 *>(t_fft_ws[1].get(n * 16));
+    double2 *tmp = static_cast<double2 *>(t_fft_ws[s].ws[1].get(n * 16));
     launch_axis(in, tmp, outer, L1, (int64_t) L2 * inner, MODE_C2C, inverse, 1.0, s);
     if (inner == 1) {
         const int64_t tiles = outer * ((L1 + 31) / 32) * ((L2 + 31) / 32);
@@ -468,7 +474,14 @@ static const double2 *bluestein_filter(int64_t L, int64_t M, int inverse, cudaSt
     bluestein_filter_kernel<<<grid_for(M), 256, 0, s>>>(B, L, M, inverse);
     check_launch("bluestein_filter_kernel");
     launch_axis(B, B, 1, (int) M, 1, MODE_C2C, 0, 1.0, s);
+    // the table becomes visible to other threads / streams only once it is complete
+    SSTC_CUDA(cudaStreamSynchronize(s));
     std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto it = g_bluestein_filters.find(key);
+    if (it != g_bluestein_filters.end()) {  // another thread built it meanwhile: keep theirs
+        cudaFree(B);
+        return it->second;
+    }
     g_bluestein_filters[key] = B;
     return B;
 }
@@ -489,7 +502,7 @@ static void bluestein_axis(const double2 *in, double2 *out, int64_t outer, int L
     for (int64_t o0 = 0; o0 < outer; o0 += planes_per_chunk) {
         const int64_t no = std::min(planes_per_chunk, outer - o0);
         const int64_t lines = no * inner;
-        double2 *Y = static_cast<double2 *>(t_fft_ws[0].get(lines * M * 16));
+        double2 *Y = static_cast<double2 *>(t_fft_ws[s].ws[0].get(lines * M * 16));
         const double2 *src = in + o0 * (int64_t) L * inner;
         double2 *dst = out + o0 * (int64_t) L * inner;
         bluestein_pre_kernel<<<grid_for(lines * M), 256, 0, s>>>(src, Y, no, L, inner, M, inverse);
@@ -519,7 +532,7 @@ static void long_axis(const void *in, void *out, int64_t outer, int L, int64_t i
     }
     // real transforms on the last axis (inner == 1, outer = lines): stage through a full complex line
     const int64_t n = outer * (int64_t) L;
-    double2 *full = static_cast<double2 *>(t_fft_ws[2].get(n * 16));
+    double2 *full = static_cast<double2 *>(t_fft_ws[s].ws[2].get(n * 16));
     if (mode == MODE_R2C) {
         real_to_complex_kernel<<<grid_for(n), 256, 0, s>>>(static_cast<const double *>(in), full, n);
         check_launch("real_to_complex_kernel");
@@ -537,33 +550,11 @@ static void long_axis(const void *in, void *out, int64_t outer, int L, int64_t i
 
 // ---- plans ----------------------------------------------------------------------------------------------
 
-struct Step {
-    int axis_len;
-    int64_t outer, inner;
-    int mode;
-    int src;  // 0 = caller's in, 1 = caller's out, 2 = workspace
-    int dst;  // 1 = caller's out, 2 = workspace
-    double scale;
-    int64_t layout[4];  // {in_plane, in_kstride, out_plane, out_kstride}; all 0 = the natural layout
-};
-
 }  // namespace sstc
-
-struct sstc_fft_plan_s {
-    int kind;
-    std::vector<int32_t> dims;
-    int64_t in_len, out_len;  // doubles
-    int inverse;
-    std::vector<sstc::Step> steps;
-    void *workspace = nullptr;
-    int64_t workspace_bytes = 0;
-    int transposed_passes = -1;  // hint: -1 auto, 0 never, 1 whenever legal
-    int alternate_order = 0;     // hint: odd passes process their tiles in descending order (measured: no gain)
-};
 
 namespace sstc {
 
-static void transform_lengths(int kind, int rank, const int32_t *dims, int64_t &in_len, int64_t &out_len) {
+void transform_lengths(int kind, int rank, const int32_t *dims, int64_t &in_len, int64_t &out_len) {
     // Plan::getTransformParameters, native/src/sharedx/Plan.cpp:230-320 (64-bit instead of jint).
     if (rank <= 0 || !dims) {
         throw std::runtime_error("Rank must be greater than zero");
@@ -596,7 +587,7 @@ static void transform_lengths(int kind, int rank, const int32_t *dims, int64_t &
     }
 }
 
-static void build_plan(sstc_fft_plan_s &p) {
+void build_plan(sstc_fft_plan_s &p) {
     p.steps.clear();
     if (p.workspace) {
         SSTC_CUDA(cudaFree(p.workspace));
@@ -709,7 +700,7 @@ static void build_plan(sstc_fft_plan_s &p) {
     }
 }
 
-static void execute_plan(sstc_fft_plan_s &p, const double *d_in, double *d_out, cudaStream_t stream) {
+void execute_plan(sstc_fft_plan_s &p, const double *d_in, double *d_out, cudaStream_t stream) {
     if (!d_in || !d_out) {
         throw std::runtime_error("Invalid arguments");
     }
@@ -808,11 +799,100 @@ static void execute_convolve(sstc_fft_plan_s &p, const double *d_spec, const dou
     }
 }
 
-// Host-tier plan cache (FftwService keeps one too: FftwService.java:58-67,221-236). Guarded by one mutex;
-// host-tier calls are PCIe-bound, so serialising them costs nothing measurable.
-static std::mutex g_host_mutex;
-static std::map<std::vector<int32_t>, sstc_fft_plan_s *> g_host_plans;
-static Scratch g_host_in, g_host_out;
+sstc_fft_plan_s *new_plan(int kind, int rank, const int32_t *dims) {
+    int64_t a = 0, b = 0;
+    transform_lengths(kind, rank, dims, a, b);
+    sstc_fft_plan_s *p = new sstc_fft_plan_s();
+    p->kind = kind;
+    p->dims.assign(dims, dims + rank);
+    p->in_len = a;
+    p->out_len = b;
+    try {
+        build_plan(*p);
+    } catch (...) {
+        if (p->workspace) {
+            cudaFree(p->workspace);
+        }
+        delete p;
+        throw;
+    }
+    return p;
+}
+
+void delete_plan(sstc_fft_plan_s *p) {
+    if (p) {
+        if (p->workspace) {
+            cudaFree(p->workspace);
+        }
+        delete p;
+    }
+}
+
+void fft_axis_pass(const void *in, void *out, int64_t outer, int L, int64_t inner, int mode, int inverse, double scale,
+        cudaStream_t stream, const int64_t *layout) {
+    static_assert(PASS_C2C == MODE_C2C && PASS_R2C == MODE_R2C && PASS_C2R == MODE_C2R, "pass modes");
+    launch_axis(in, out, outer, L, inner, mode, inverse ? 1 : 0, scale, stream, Blocks(), Blocks(), layout);
+}
+
+static void scatter_common(FftPassArgs &a, const double *d_in, void *const *d_out_blocks, int nblocks, int32_t len,
+        int inverse, double scale, int64_t max_ctas, int bulk) {
+    if (!(len >= 8 && len <= 4096 && (len & (len - 1)) == 0)) {
+        throw std::runtime_error("line scatter needs a power-of-two length between 8 and 4096");
+    }
+    memset(&a, 0, sizeof(a));
+    a.in = reinterpret_cast<const double2 *>(d_in);
+    a.tw = pow2_twiddles_for(len);
+    a.inner = 1;
+    a.in_plane = a.out_plane = len;
+    a.in_kstride = a.out_kstride = 1;
+    a.scale = scale;
+    a.mode = MODE_C2C;
+    a.inverse = inverse ? 1 : 0;
+    a.blk_pitch = a.in_blk_pitch = 1;
+    for (int q = 0; q < nblocks; q++) {
+        a.blk[q] = static_cast<double2 *>(d_out_blocks[q]);
+    }
+    a.ls_nblk = nblocks;
+    a.grid_limit = max_ctas > 0 ? max_ctas : 0;
+    a.ls_bulk = bulk ? 1 : 0;
+}
+
+void fft_lines_scatter(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes, int32_t plane_lines,
+        int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas, int bulk, cudaStream_t stream) {
+    if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || planes < 0 || plane_lines <= 0 || len <= 0 ||
+            plane_lines % nblocks != 0 || first < 0 || group <= 0 || first + group > plane_lines / nblocks) {
+        throw std::runtime_error("Invalid arguments");
+    }
+    FftPassArgs a;
+    scatter_common(a, d_in, d_out_blocks, nblocks, len, inverse, scale, max_ctas, bulk);
+    if (planes == 0) {
+        return;
+    }
+    a.outer = planes * nblocks * (int64_t) group;  // lines in this launch
+    a.ls_group = group;
+    a.ls_first = first;
+    a.ls_block_lines = plane_lines / nblocks;
+    a.ls_plane_lines = plane_lines;
+    dispatch_axis(a, len, false, stream);
+}
+
+void fft_planes_scatter(const double *d_in, void *const *d_out_blocks, int nblocks, int32_t block_planes, int32_t plane_lines,
+        int32_t dst_plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
+        int bulk, cudaStream_t stream) {
+    if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || block_planes <= 0 || plane_lines <= 0 ||
+            dst_plane_lines < plane_lines || len <= 0 || first < 0 || group <= 0 || first + group > block_planes) {
+        throw std::runtime_error("Invalid arguments");
+    }
+    FftPassArgs a;
+    scatter_common(a, d_in, d_out_blocks, nblocks, len, inverse, scale, max_ctas, bulk);
+    a.outer = (int64_t) nblocks * group * plane_lines;  // lines in this launch
+    a.ls_group = group;
+    a.ls_first = first;
+    a.ls_block_lines = block_planes;
+    a.ls_plane_lines = dst_plane_lines;
+    a.ls_sub = plane_lines;
+    dispatch_axis(a, len, false, stream);
+}
 
 }  // namespace sstc
 
@@ -839,23 +919,7 @@ int sstc_fft_plan_create(sstc_fft_plan *plan, int kind, int rank, const int32_t 
             throw std::runtime_error("Invalid arguments");
         }
         *plan = nullptr;
-        int64_t a = 0, b = 0;
-        transform_lengths(kind, rank, dims, a, b);
-        sstc_fft_plan_s *p = new sstc_fft_plan_s();
-        p->kind = kind;
-        p->dims.assign(dims, dims + rank);
-        p->in_len = a;
-        p->out_len = b;
-        try {
-            build_plan(*p);
-        } catch (...) {
-            if (p->workspace) {
-                cudaFree(p->workspace);
-            }
-            delete p;
-            throw;
-        }
-        *plan = p;
+        *plan = new_plan(kind, rank, dims);
     });
 }
 
@@ -939,38 +1003,8 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
         int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
         void *stream) {
     return guarded([&] {
-        if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || planes < 0 || plane_lines <= 0 || len <= 0 ||
-                plane_lines % nblocks != 0 || first < 0 || group <= 0 || first + group > plane_lines / nblocks) {
-            throw std::runtime_error("Invalid arguments");
-        }
-        if (!(len >= 8 && len <= 4096 && (len & (len - 1)) == 0)) {
-            throw std::runtime_error("line scatter needs a power-of-two length between 8 and 4096");
-        }
-        if (planes == 0) {
-            return;
-        }
-        FftPassArgs a;
-        memset(&a, 0, sizeof(a));
-        a.in = reinterpret_cast<const double2 *>(d_in);
-        a.tw = pow2_twiddles_for(len);
-        a.outer = planes * nblocks * (int64_t) group;  // lines in this launch
-        a.inner = 1;
-        a.in_plane = a.out_plane = len;
-        a.in_kstride = a.out_kstride = 1;
-        a.scale = scale;
-        a.mode = MODE_C2C;
-        a.inverse = inverse ? 1 : 0;
-        a.blk_pitch = a.in_blk_pitch = 1;
-        for (int q = 0; q < nblocks; q++) {
-            a.blk[q] = static_cast<double2 *>(d_out_blocks[q]);
-        }
-        a.ls_group = group;
-        a.ls_nblk = nblocks;
-        a.ls_first = first;
-        a.ls_block_lines = plane_lines / nblocks;
-        a.ls_plane_lines = plane_lines;
-        a.grid_limit = max_ctas > 0 ? max_ctas : 0;
-        dispatch_axis(a, len, false, as_stream(stream));
+        fft_lines_scatter(d_in, d_out_blocks, nblocks, planes, plane_lines, len, first, group, inverse, scale, max_ctas, 0,
+                as_stream(stream));
     });
 }
 
@@ -978,36 +1012,8 @@ int sstc_fft_planes_scatter_dev(const double *d_in, void *const *d_out_blocks, i
         int32_t plane_lines, int32_t dst_plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale,
         int64_t max_ctas, void *stream) {
     return guarded([&] {
-        if (!d_in || !d_out_blocks || nblocks <= 0 || nblocks > 8 || block_planes <= 0 || plane_lines <= 0 ||
-                dst_plane_lines < plane_lines || len <= 0 || first < 0 || group <= 0 || first + group > block_planes) {
-            throw std::runtime_error("Invalid arguments");
-        }
-        if (!(len >= 8 && len <= 4096 && (len & (len - 1)) == 0)) {
-            throw std::runtime_error("line scatter needs a power-of-two length between 8 and 4096");
-        }
-        FftPassArgs a;
-        memset(&a, 0, sizeof(a));
-        a.in = reinterpret_cast<const double2 *>(d_in);
-        a.tw = pow2_twiddles_for(len);
-        a.outer = (int64_t) nblocks * group * plane_lines;  // lines in this launch
-        a.inner = 1;
-        a.in_plane = a.out_plane = len;
-        a.in_kstride = a.out_kstride = 1;
-        a.scale = scale;
-        a.mode = MODE_C2C;
-        a.inverse = inverse ? 1 : 0;
-        a.blk_pitch = a.in_blk_pitch = 1;
-        for (int q = 0; q < nblocks; q++) {
-            a.blk[q] = static_cast<double2 *>(d_out_blocks[q]);
-        }
-        a.ls_group = group;
-        a.ls_nblk = nblocks;
-        a.ls_first = first;
-        a.ls_block_lines = block_planes;
-        a.ls_plane_lines = dst_plane_lines;
-        a.ls_sub = plane_lines;
-        a.grid_limit = max_ctas > 0 ? max_ctas : 0;
-        dispatch_axis(a, len, false, as_stream(stream));
+        fft_planes_scatter(d_in, d_out_blocks, nblocks, block_planes, plane_lines, dst_plane_lines, len, first, group,
+                inverse, scale, max_ctas, 0, as_stream(stream));
     });
 }
 
@@ -1027,49 +1033,6 @@ int sstc_fft_axis_blocked_dev(void *const *d_in_blocks, int n_in, int64_t in_pit
         bout.pitch = out_pitch;
         launch_axis(nullptr, nullptr, outer, len, inner, MODE_C2C, inverse ? 1 : 0, scale, as_stream(stream), bin,
                 bout);
-    });
-}
-
-int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t in_len, double *out,
-        int64_t out_len) {
-    return guarded([&] {
-        if (!in || !out) {
-            throw std::runtime_error("Invalid arguments");
-        }
-        int64_t a = 0, b = 0;
-        transform_lengths(kind, rank, dims, a, b);
-        if (in_len != a || out_len != b) {
-            // Plan.cpp:88-90
-            throw std::runtime_error("Input and/or output arrays do not have expected sizes");
-        }
-        std::lock_guard<std::mutex> lock(g_host_mutex);
-        std::vector<int32_t> key;
-        key.push_back(kind);
-        key.insert(key.end(), dims, dims + rank);
-        sstc_fft_plan_s *p = nullptr;
-        auto it = g_host_plans.find(key);
-        if (it == g_host_plans.end()) {
-            p = new sstc_fft_plan_s();
-            p->kind = kind;
-            p->dims.assign(dims, dims + rank);
-            p->in_len = a;
-            p->out_len = b;
-            try {
-                build_plan(*p);
-            } catch (...) {
-                delete p;
-                throw;
-            }
-            g_host_plans[key] = p;
-        } else {
-            p = it->second;
-        }
-        double *d_in = static_cast<double *>(g_host_in.get(a * 8));
-        double *d_out = static_cast<double *>(g_host_out.get(b * 8));
-        SSTC_CUDA(cudaMemcpyAsync(d_in, in, (size_t) a * 8, cudaMemcpyHostToDevice, 0));
-        execute_plan(*p, d_in, d_out, 0);
-        SSTC_CUDA(cudaMemcpyAsync(out, d_out, (size_t) b * 8, cudaMemcpyDeviceToHost, 0));
-        SSTC_CUDA(cudaStreamSynchronize(0));
     });
 }
 

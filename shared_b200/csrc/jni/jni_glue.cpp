@@ -156,7 +156,9 @@ void move_objects(JNIEnv *env, bool is_map, jintArray spec, jobjectArray src, ji
             so += (jlong) lists[d][idx[d]].first * sS[d];
             dof += (jlong) lists[d][idx[d]].second * dS[d];
         }
-        env->SetObjectArrayElement(dst, (jsize) dof, env->GetObjectArrayElement(src, (jsize) so));
+        jobject ref = env->GetObjectArrayElement(src, (jsize) so);
+        env->SetObjectArrayElement(dst, (jsize) dof, ref);
+        env->DeleteLocalRef(ref);  // O(total) local references otherwise: the JVM only guarantees 16 per native frame
         for (size_t d = nd; d-- > 0;) {
             if (++idx[d] < lists[d].size()) {
                 break;
@@ -615,8 +617,10 @@ jobject new_sparse_state(JNIEnv *env, const sstc_sparse_state &st, Kind kind, jo
         jobjectArray a = comp ? env->NewObjectArray(st.count, comp, nullptr) : nullptr;
         const int32_t *pos = static_cast<const int32_t *>(st.values);
         for (jsize i = 0; a && i < st.count; i++) {
-            env->SetObjectArrayElement(a, i, pos[i] < n_first ? env->GetObjectArrayElement(first, pos[i])
-                                                              : env->GetObjectArrayElement(second, pos[i] - n_first));
+            jobject ref = pos[i] < n_first ? env->GetObjectArrayElement(first, pos[i])
+                                           : env->GetObjectArrayElement(second, pos[i] - n_first);
+            env->SetObjectArrayElement(a, i, ref);
+            env->DeleteLocalRef(ref);
         }
         values = a;
     }

@@ -44,6 +44,7 @@ struct JNIEnv_ {
     jboolean ExceptionCheck();
     jobject NewGlobalRef(jobject obj);
     void DeleteGlobalRef(jobject obj);
+    void DeleteLocalRef(jobject obj);
     jboolean IsInstanceOf(jobject obj, jclass clazz);
     jsize GetArrayLength(jarray array);
     void *GetPrimitiveArrayCritical(jarray array, jboolean *isCopy);

@@ -1,5 +1,8 @@
 // sstc_core.cu -- library lifecycle, error reporting and device-memory helpers of the C ABI.
+#include <stdlib.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "sstc_internal.h"
 
@@ -11,21 +14,58 @@ std::atomic<int64_t> g_launch_count{0};
 void set_last_error(const std::string &msg) { t_last_error = msg; }
 void clear_last_error() { t_last_error.clear(); }
 
+static std::atomic<int> g_device{-1};
+static thread_local int t_bound_device = -1;
+static std::atomic<bool> g_process_exiting{false};
+
+void bind_thread_device() {
+    const int dev = g_device.load(std::memory_order_relaxed);
+    if (dev >= 0 && t_bound_device != dev) {
+        SSTC_CUDA(cudaSetDevice(dev));
+        t_bound_device = dev;
+    }
+}
+
 void *Scratch::get(int64_t need) {
+    int cur = 0;
+    SSTC_CUDA(cudaGetDevice(&cur));
+    if (ptr && device != cur) {
+        release();
+    }
     if (need > bytes) {
-        if (ptr) {
-            cudaFree(ptr);
-            ptr = nullptr;
-            bytes = 0;
-        }
+        release();
         SSTC_CUDA(cudaMalloc(&ptr, (size_t) need));
         bytes = need;
+        device = cur;
     }
     return ptr;
 }
 
+void Scratch::release() {
+    if (ptr) {
+        int cur = -1;
+        const bool moved = cudaGetDevice(&cur) == cudaSuccess && cur != device && device >= 0;
+        if (moved) {
+            cudaSetDevice(device);
+        }
+        cudaFree(ptr);  // errors ignored: at process exit the runtime may already be unloading
+        if (moved) {
+            cudaSetDevice(cur);
+        }
+        (void) cudaGetLastError();
+    }
+    ptr = nullptr;
+    bytes = 0;
+    device = -1;
+}
+
 Scratch::~Scratch() {
-    // Process teardown: the CUDA context may already be gone; leak rather than call into a dead runtime.
+    // A worker thread that exits hands its staging buffers back (a JVM that churns threads would otherwise strand
+    // them in HBM). During process teardown (static destructors, after exit() has begun) the CUDA runtime may already
+    // be gone: leak then rather than call into it.
+    if (!g_process_exiting.load()) {
+        release();
+    }
 }
 
 // Cross-GPU barrier for the one-process-per-GPU slab transform: every rank owns an array of 8 epoch slots that
@@ -34,11 +74,42 @@ Scratch::~Scratch() {
 // stream, so those stores are complete before the flag is written. One kernel per rank, each on its own GPU,
 // so the waiting ranks are always co-resident. A bounded spin (~4 s) turns a missing peer into stale data the
 // parity checks catch rather than a hung device.
+// sound or loud: a rank that gives up waiting records (epoch, missing rank) in a host-mapped word that every later
+// entry point of the library checks (check_barrier_error), so the transform whose barrier failed -- or at the latest
+// the next call -- raises instead of returning a slab that peers were still writing.
+static unsigned long long *g_barrier_err_host = nullptr, *g_barrier_err_dev[16] = {nullptr};
+static std::mutex g_barrier_err_mutex;
+
+static unsigned long long *barrier_error_word() {
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_barrier_err_mutex);
+    if (!g_barrier_err_host) {
+        SSTC_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g_barrier_err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        *g_barrier_err_host = 0;
+    }
+    if (!g_barrier_err_dev[dev & 15]) {
+        SSTC_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&g_barrier_err_dev[dev & 15]), g_barrier_err_host, 0));
+    }
+    return g_barrier_err_dev[dev & 15];
+}
+
+void barrier_error_word_prepare() { (void) barrier_error_word(); }
+
+void check_barrier_error() {
+    if (g_barrier_err_host && *reinterpret_cast<volatile unsigned long long *>(g_barrier_err_host) != 0) {
+        const unsigned long long w = *reinterpret_cast<volatile unsigned long long *>(g_barrier_err_host);
+        *reinterpret_cast<volatile unsigned long long *>(g_barrier_err_host) = 0;
+        throw std::runtime_error("peer barrier timed out: rank " + std::to_string((w >> 8) & 0xff) + " never saw rank " +
+                std::to_string(w & 0xff) + " arrive (epoch " + std::to_string(w >> 16) + "); the slab it guards is invalid");
+    }
+}
+
 struct PeerFlags {
     unsigned long long *ptr[8];
 };
 
-__global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned long long epoch) {
+__global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned long long epoch, unsigned long long *err) {
     const int r = threadIdx.x;
     if (epoch == 0) {
         // self-counting mode (CUDA-graph friendly: no per-launch argument changes): slot 8 of the rank's own
@@ -60,11 +131,24 @@ __global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned 
     volatile unsigned long long *local = f.ptr[rank] + r;
     const long long start = clock64();
     while (*local < epoch) {
-        if (clock64() - start > 8000000000LL) {
+        if (clock64() - start > 8000000000LL) {  // ~4 s: a peer died or never issued its barrier
+            if (err) {
+                *reinterpret_cast<volatile unsigned long long *>(err) = (epoch << 16) | ((unsigned long long) rank << 8) | (unsigned long long) r;
+                __threadfence_system();
+            }
             break;
         }
     }
     __threadfence_system();
+}
+
+void launch_peer_barrier(void *const *flag_arrays, int nranks, int rank, unsigned long long epoch, cudaStream_t stream) {
+    PeerFlags f;
+    for (int r = 0; r < 8; r++) {
+        f.ptr[r] = r < nranks ? static_cast<unsigned long long *>(flag_arrays[r]) : nullptr;
+    }
+    peer_barrier_kernel<<<1, 32, 0, stream>>>(f, nranks, rank, epoch, barrier_error_word());
+    check_launch("peer_barrier_kernel");
 }
 
 }  // namespace sstc
@@ -85,6 +169,10 @@ int sstc_init(int device) {
             throw std::runtime_error("Invalid device");
         }
         SSTC_CUDA(cudaSetDevice(device));
+        g_device.store(device);
+        t_bound_device = device;
+        static std::once_flag exit_hook;
+        std::call_once(exit_hook, [] { atexit([] { g_process_exiting.store(true); }); });
         cudaDeviceProp prop;
         SSTC_CUDA(cudaGetDeviceProperties(&prop, device));
         if (prop.major != 10) {
@@ -202,17 +290,16 @@ int sstc_peer_barrier_dev(void *const *d_flag_arrays, int nranks, int rank, uint
         if (!d_flag_arrays || nranks <= 0 || nranks > 8 || rank < 0 || rank >= nranks) {
             throw std::runtime_error("Invalid arguments");
         }
-        PeerFlags f;
-        for (int r = 0; r < 8; r++) {
-            f.ptr[r] = r < nranks ? static_cast<unsigned long long *>(d_flag_arrays[r]) : nullptr;
-        }
-        peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, nranks, rank, (unsigned long long) epoch);
-        check_launch("peer_barrier_kernel");
+        check_barrier_error();
+        launch_peer_barrier(d_flag_arrays, nranks, rank, (unsigned long long) epoch, as_stream(stream));
     });
 }
 
 int sstc_stream_sync(void *stream) {
-    return guarded([&] { SSTC_CUDA(cudaStreamSynchronize(as_stream(stream))); });
+    return guarded([&] {
+        SSTC_CUDA(cudaStreamSynchronize(as_stream(stream)));
+        check_barrier_error();
+    });
 }
 
 }  // extern "C"

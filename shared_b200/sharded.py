@@ -16,7 +16,8 @@ Three exchange modes:
                   z lines straight into the owner's receive buffer over NVLink (CUDA IPC mapping), in G groups of
                   y indices. After each group a flag barrier kernel runs on a side stream and the x pass of that
                   group's columns starts on a third stream, so the x pass (HBM-bound) overlaps the remaining
-                  exchange (NVLink-bound). forward() only.
+                  exchange (NVLink-bound). The schedule itself (streams, events, CUDA graphs) lives behind the C ABI
+                  (sstc_slab_*, shared_b200/csrc/fft_slab.cu); this class only maps the peers' buffers and calls it.
     "p2p"         z pass, then the y pass scatters 128-byte row segments into the peers' receive buffers; one
                   cross-rank barrier, then the x pass. Also implements inverse().
     "collective"  destination blocks are a local send buffer; torch.distributed all_to_all_single moves them
@@ -146,7 +147,7 @@ class SlabFft3d:
     """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
 
     def __init__(self, dims, group=None, exchange="pipe", engine=None, device=None, groups=None,
-                 exchange_ctas=None, chunks=None):
+                 exchange_ctas=None, chunks=None, bulk_store=None, graph=None):
         if len(dims) != 3:
             raise ValueError("SlabFft3d needs three dimensions")
         self.group = group
@@ -164,26 +165,30 @@ class SlabFft3d:
         self.work = self.engine.empty(self.n_local)
         self._step = 0
         self.replayed_kernels = 0  # kernels launched through CUDA-graph replays (not seen by sstc_launch_count)
+        self._slab = None
+        if exchange == "pipe" and not (8 <= self.d2 <= 4096 and self.d2 & (self.d2 - 1) == 0):
+            exchange = self.exchange = "p2p"  # the line scatter needs a power-of-two d2 the tile kernels hold
         if exchange in ("p2p", "pipe"):
             dev = self.engine.device
             self.peer = [PeerBuffer(self.n_local, dev, group) for _ in range(2)]
             self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
-            self.groups = next(g for g in (groups or 4, 4, 2, 1) if self.y_loc % g == 0)
-            # measured on B200s (512^3, tools/sweep_sharded.py): at 4 and 8 ranks one exchange CTA per SM keeps NVLink
-            # busy (74 do not) and leaves room for the x pass to run beside it (uncapped: 0.55 vs 0.51 ms at 8); at 2
-            # ranks the exchange pass moves half of the data and wants two per SM (1.40 vs 1.54 ms)
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            self.exchange_ctas = (sms * (2 if self.world == 2 else 1)) if exchange_ctas is None else int(exchange_ctas)
-            self.flags = PeerBuffer(16, dev, group)  # 8 uint64 epoch slots per rank (+ padding)
+            self.flags = PeerBuffer(16, dev, group)  # 8 uint64 epoch slots per rank (+ the rank's own call counter)
             self.flags.tensor.zero_()
             torch.cuda.synchronize(dev)
             dist.barrier(group)
-            self._epoch = 0
-            # measured (tools/sweep_sharded.py): chunking group 0 gains 2.5 % at 8 ranks (0.518 -> 0.506 ms), nothing at 2
-            self.chunks = next(c for c in (chunks or (4 if self.world >= 8 else 1), 1) if self.x_loc % c == 0)
-            self.s_z = torch.cuda.Stream(dev)
-            self.s_bar = torch.cuda.Stream(dev, priority=-1)
-            self.s_x = torch.cuda.Stream(dev, priority=-1)  # its CTAs must win SM slots from the pending exchange CTAs
+            if exchange == "pipe":
+                lib = _lib.lib()
+                arr = lambda ptrs: (ctypes.c_void_p * len(ptrs))(*[int(q) for q in ptrs])
+                h = ctypes.c_void_p()
+                _lib.check(lib.sstc_slab_create(ctypes.byref(h), _lib.i32_array([self.d0, self.d1, self.d2]), p, self.rank,
+                                                arr(self.peer[0].ptrs), arr(self.peer[1].ptrs), arr(self.flags.ptrs)))
+                self._slab = h
+                for name, value in (("groups", groups), ("exchange_ctas", exchange_ctas), ("chunks", chunks),
+                                    ("bulk_store", bulk_store), ("graph", graph)):
+                    if value is not None:
+                        _lib.check(lib.sstc_slab_set_option(h, name.encode(), int(value)))
+                torch.cuda.synchronize(dev)
+                dist.barrier(group)
         elif exchange == "collective":
             self.send = self.engine.empty(self.n_local)
             self.recv = self.engine.empty(self.n_local)
@@ -197,86 +202,31 @@ class SlabFft3d:
         dist.all_reduce(self._flag, op=dist.ReduceOp.MAX, group=self.group)
 
     # -- transforms ---------------------------------------------------------------------------------------
-    def _forward_pipe(self, x):
-        e, p = self.engine, self.world
-        dev = e.device
-        cur = torch.cuda.current_stream(dev)
-        buf = self.peer[self._step % 2]
-        self._step += 1
-        base = [buf.ptrs[q] + self.rank * self.block * 16 for q in range(p)]
-        yg = self.y_loc // self.groups
-        cols = yg * self.d2                      # columns of the received (d0, y_loc*d2) array per group
-        kstride = self.y_loc * self.d2
-        # y pass, local, in C chunks of planes. The exchange pass runs in G groups of y indices; group 0 is issued
-        # chunk by chunk, each chunk as soon as its planes have left the y pass, so the exchange starts after 1/C of
-        # the y pass instead of after all of it; groups 1.. cover all planes at once. After every group a barrier,
-        # then the x pass of that group's columns beside the rest of the exchange.
-        C, xc = self.chunks, self.x_loc // self.chunks
-        plane = self.d1 * self.d2
-        x_ptr, w_ptr = x.data_ptr(), self.work.data_ptr()
-        y_done = []
-        for c in range(C):
-            off = c * xc * plane * 16
-            e.axis(x_ptr + off, w_ptr + off, xc, self.d1, self.d2)                                # y, local
-            y_done.append(cur.record_event())
-        with torch.cuda.stream(self.s_z):
-            for g in range(self.groups):
-                if g == 0:
-                    for c in range(C):
-                        self.s_z.wait_event(y_done[c])
-                        src = w_ptr + c * xc * plane * 16
-                        dst = [b + c * xc * kstride * 16 for b in base]
-                        e.lines_scatter(src, dst, xc, self.d1, self.d2, 0, yg, max_ctas=self.exchange_ctas)
-                else:
-                    e.lines_scatter(w_ptr, base, self.x_loc, self.d1, self.d2, g * yg, yg,
-                                    max_ctas=self.exchange_ctas)                                  # z + transpose
-                sent = self.s_z.record_event()
-                self.s_bar.wait_event(sent)
-                with torch.cuda.stream(self.s_bar):
-                    e.peer_barrier(self.flags.ptrs, self.rank, 0)  # self-counting epochs: graph-capturable
-                    arrived = self.s_bar.record_event()
-                self.s_x.wait_event(arrived)
-                with torch.cuda.stream(self.s_x):
-                    ptr = buf.local_ptr + g * cols * 16
-                    e.axis_strided(ptr, ptr, 1, self.d0, cols, 0, kstride, 0, kstride)           # x on this group
-        cur.wait_stream(self.s_x)
-        return buf.tensor
+    def _run_slab(self, fn, x):
+        out = ctypes.c_void_p()
+        stream = torch.cuda.current_stream(self.engine.device).cuda_stream
+        _lib.check(fn(self._slab, ctypes.c_void_p(int(x.data_ptr())), ctypes.byref(out), ctypes.c_void_p(stream)))
+        for b in self.peer:
+            if b.local_ptr == out.value:
+                return b.tensor
+        raise RuntimeError("sstc_slab returned a pointer outside its receive buffers")
 
     def capture(self, x):
-        """Record the pipelined forward schedule for input buffer `x` into two CUDA graphs (one per receive
-        buffer) so that a step costs one graph launch instead of ~3G+1 Python-issued launches."""
+        """Two eager steps with input buffer `x` (one per receive buffer): from the third call on, the C side replays
+        the schedule from a CUDA graph (sstc_slab_forward records one per input pointer and buffer parity)."""
         if self.exchange != "pipe":
             raise ValueError("capture() is for the 'pipe' exchange")
-        dev = self.engine.device
-        for _ in range(2 + self._step % 2):  # warm up both parities eagerly (first-use attribute calls are not
-            self._forward_pipe(x)            # capturable) and leave the buffer parity at 0
-        torch.cuda.synchronize(dev)
-        dist.barrier(self.group)
-        self._graphs, self._graph_out, self._graph_in = [], [], x.data_ptr()
-        side = torch.cuda.Stream(dev)
-        for parity in range(2):
-            assert self._step % 2 == parity
-            g = torch.cuda.CUDAGraph()
-            before = _lib.lib().sstc_launch_count()
-            with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
-                out = self._forward_pipe(x)
-            self.graph_kernels = int(_lib.lib().sstc_launch_count() - before)  # kernels one replay launches
-            self._graphs.append(g)
-            self._graph_out.append(out)
-        torch.cuda.synchronize(dev)
+        for _ in range(2):
+            self.forward(x)
+        torch.cuda.synchronize(self.engine.device)
         dist.barrier(self.group)
 
     def forward(self, x):
-        """x: this rank's natural slab, (n_local, 2) float64. Returns this rank's transposed slab (a view
-        of an internal buffer, valid until the next-but-one call)."""
+        """x: this rank's natural slab, (n_local, 2) float64. Returns this rank's transposed slab: a view of an
+        internal receive buffer, valid until the next-but-one call provided its consumers are enqueued on the current
+        stream before the next call (peers write into it again two calls later; include/sst_cuda.h, sstc_slab)."""
         if self.exchange == "pipe":
-            if getattr(self, "_graphs", None) and x.data_ptr() == self._graph_in:
-                parity = self._step % 2
-                self._step += 1
-                self._graphs[parity].replay()
-                self.replayed_kernels += self.graph_kernels
-                return self._graph_out[parity]
-            return self._forward_pipe(x)
+            return self._run_slab(_lib.lib().sstc_slab_forward, x)
         e, p = self.engine, self.world
         e.axis(x, self.work, self.x_loc * self.d1, self.d2, 1)                                   # z
         if self.exchange == "p2p":
@@ -293,42 +243,10 @@ class SlabFft3d:
         e.axis(out, out, 1, self.d0, self.y_loc * self.d2)                                       # x
         return out
 
-    def _inverse_pipe(self, y):
-        """The forward pipeline mirrored: x pass locally (y is preserved), then the z pass is the exchange pass -- it
-        stores whole lines into the owners' natural slabs, plane group by plane group -- and after each group's
-        barrier the y pass (with the 1/N scale) runs on that group's planes beside the rest of the exchange."""
-        e, p = self.engine, self.world
-        dev = e.device
-        cur = torch.cuda.current_stream(dev)
-        buf = self.peer[self._step % 2]
-        self._step += 1
-        e.axis(y, self.work, 1, self.d0, self.y_loc * self.d2, inverse=True)                      # x, local
-        x_done = cur.record_event()
-        base = [buf.ptrs[q] + self.rank * self.y_loc * self.d2 * 16 for q in range(p)]
-        ng = next(g for g in (self.groups, 4, 2, 1) if self.x_loc % g == 0)
-        xg = self.x_loc // ng
-        plane = self.d1 * self.d2
-        with torch.cuda.stream(self.s_z):
-            self.s_z.wait_event(x_done)
-            for g in range(ng):
-                e.planes_scatter(self.work, base, self.x_loc, self.y_loc, self.d1, self.d2, g * xg, xg, inverse=True,
-                                 max_ctas=self.exchange_ctas)                                      # z + transpose
-                sent = self.s_z.record_event()
-                self.s_bar.wait_event(sent)
-                with torch.cuda.stream(self.s_bar):
-                    e.peer_barrier(self.flags.ptrs, self.rank, 0)
-                    arrived = self.s_bar.record_event()
-                self.s_x.wait_event(arrived)
-                with torch.cuda.stream(self.s_x):
-                    ptr = buf.local_ptr + g * xg * plane * 16
-                    e.axis(ptr, ptr, xg, self.d1, self.d2, inverse=True, scale=1.0 / self.n_total)  # y on this group
-        cur.wait_stream(self.s_x)
-        return buf.tensor
-
     def inverse(self, y):
         """y: this rank's transposed slab. Returns this rank's natural slab of ifft (scaled by 1/N)."""
         if self.exchange == "pipe":
-            return self._inverse_pipe(y)
+            return self._run_slab(_lib.lib().sstc_slab_inverse, y)
         e, p = self.engine, self.world
         row = self.d1 * self.d2  # one x row of a natural slab
         if self.exchange in ("p2p", "pipe"):
@@ -355,6 +273,10 @@ class SlabFft3d:
         return 3
 
     def close(self):
+        if self._slab is not None:
+            torch.cuda.synchronize(self.engine.device)
+            _lib.lib().sstc_slab_destroy(self._slab)
+            self._slab = None
         if self.exchange in ("p2p", "pipe"):
             for b in self.peer + [self.flags]:
                 b.close()
@@ -365,3 +287,61 @@ def gather_transposed(shards, dims):
     d0, d1, d2 = dims
     p = len(shards)
     return torch.cat([s.reshape(d0, d1 // p, d2, 2) for s in shards], dim=1)
+
+
+class ShardedFft3d:
+    """The slab transform driven from ONE process over several devices (sstc_fft3d_sharded_*): what a JVM-side
+    CudaFftService binds when setHint("devices", ...) names more than one GPU. Device tier: lists of per-device slabs;
+    host tier: whole host arrays in natural order, every device moving its slab over its own PCIe link."""
+
+    def __init__(self, dims, devices):
+        self.dims = tuple(int(d) for d in dims)
+        self.devices = [int(d) for d in devices]
+        for d in self.devices:
+            _lib.init(d)
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().sstc_fft3d_sharded_create(ctypes.byref(h), _lib.i32_array(self.dims), len(self.devices),
+                                                        _lib.i32_array(self.devices)))
+        self._h = h
+        d0, d1, d2 = self.dims
+        self.n_local = d0 * d1 * d2 // len(self.devices)
+
+    def set_option(self, name, value):
+        _lib.check(_lib.lib().sstc_fft3d_sharded_set_option(self._h, name.encode(), int(value)))
+
+    def _run(self, fn, slabs):
+        p = len(self.devices)
+        ins = (ctypes.c_void_p * p)(*[int(t.data_ptr()) for t in slabs])
+        outs = (ctypes.c_void_p * p)()
+        streams = (ctypes.c_void_p * p)(*[torch.cuda.current_stream(torch.device("cuda", d)).cuda_stream
+                                          for d in self.devices])
+        _lib.check(fn(self._h, ins, outs, streams))
+        return [torch.as_tensor(_DeviceArray(outs[r], self.n_local), device=torch.device("cuda", d))
+                for r, d in enumerate(self.devices)]
+
+    def forward(self, slabs):
+        """slabs[r]: rank r's natural slab on devices[r], (n_local, 2) float64. Returns the transposed slabs (views of
+        the plan's receive buffers, valid until the next-but-one call)."""
+        return self._run(_lib.lib().sstc_fft3d_sharded_forward, slabs)
+
+    def inverse(self, slabs):
+        return self._run(_lib.lib().sstc_fft3d_sharded_inverse, slabs)
+
+    def sync(self):
+        _lib.check(_lib.lib().sstc_fft3d_sharded_sync(self._h))
+
+    def host(self, in_, out, inverse=False):
+        """Whole-array transform on host arrays (numpy float64, interleaved complex, natural order in and out)."""
+        _lib.check(_lib.lib().sstc_fft3d_sharded_host(self._h, int(bool(inverse)), ctypes.c_void_p(in_.ctypes.data),
+                                                      ctypes.c_void_p(out.ctypes.data)))
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _lib.lib().sstc_fft3d_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

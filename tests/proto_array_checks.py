@@ -1,7 +1,7 @@
 """The reference's structural-operation tests (RealArrayTest.java:58-720, IntegerArrayTest.java:52-222, ArrayFftTest's
 fftShift) as checks over ANY ArrayKernel provider `k`, run through shared_b200.proto_array.ProtoArray. tests/
 test_proto_array.py hands in the reference's native kernel (CPU); the GPU replay over CudaArrayKernel is
-tests/pending_gpu/proto_array_gpu.py until it has been run once on a B200."""
+tests/test_proto_array_gpu.py (over CudaArrayKernel, on a B200)."""
 import numpy as np
 import pytest
 

@@ -22,7 +22,7 @@ def test_header_declares_and_library_exports():
     for n in names:
         assert hasattr(handle, n), "libsst_cuda.so does not export " + n
         assert n in _lib.SIGNATURES, "no ctypes signature for " + n
-    assert handle.sstc_abi_version() == 1
+    assert handle.sstc_abi_version() == 2
 
 
 def test_lengths_follow_plan_rules():

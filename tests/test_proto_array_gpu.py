@@ -1,4 +1,4 @@
-"""PENDING (see README.md in this directory): the reference's structural-operation KATs through ProtoArray over the CUDA
+"""The reference's structural-operation KATs through ProtoArray over the CUDA
 provider. Same checks as tests/test_proto_array.py, which runs them over the reference's native kernel on the CPU."""
 import os
 import sys
@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import proto_array_checks as pc  # noqa: E402
 from conftest import golden  # noqa: E402
 

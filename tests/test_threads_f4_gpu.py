@@ -1,4 +1,4 @@
-"""PENDING (see README.md in this directory): eigs / insertSparse / sliceSparse called from several threads at once
+"""eigs / insertSparse / sliceSparse called from several threads at once
 (per-thread scratch and result buffers; SURVEY.md 8b "Threading"). Every result must equal the one computed alone."""
 import os
 import sys
@@ -7,7 +7,7 @@ import threading
 import numpy as np
 import pytest
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from eigs_cases import cases as eigs_cases  # noqa: E402
 from sparse_cases import insert_cases, run_insert, run_slice, slice_cases  # noqa: E402
 
