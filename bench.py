@@ -15,12 +15,21 @@ Keys beyond the base contract:
                 back-to-back steps, against MEASURED_PEAKS.json's HBM copy bandwidth; `passes` lists all three
                 launches and `slowest_pass` the worst of them
   cpu_baseline  the CPU oracle (C restatement of the reference's single-threaded FftOps.java) timed on this
-                box's host on a bounded sample (N = 1 only)
-  e2e           the same transform through the host-tier C ABI call a JNI caller makes (sstc_fft): pinned host
-                arrays in, H2D + kernels + D2H inside the timed region
+                box's host on a bounded sample (N = 1 only); `all_cores` = that many independent transforms at once
+  e2e           the same transform through the host-tier C ABI call a JNI caller makes (sstc_fft) from pinned host
+                arrays, H2D + kernels + D2H inside the timed region. Every output depends on every input, so ONE
+                synchronous call cannot take less than H2D + D2H (2 x 39 ms at this pool's 55 GB/s): `single_caller`
+                reports that latency. `value` is the throughput of TWO caller threads, each making the same
+                synchronous call (the SPI is thread-safe; the host tier gives every call its own slot), so that one
+                transform's D2H overlaps the other's H2D on the full-duplex link. `pageable` repeats both with plain
+                (unpinned) arrays, which is what a JVM heap array is. The reference arm uses the same two-caller client.
+  parity        (N > 1) the step that is timed -- the recorded CUDA-graph replay -- checked outside the timed region
+                against the 1-GPU plan on the gathered input, plus the forward -> inverse round trip
+  extra_configs BASELINE.json's other configs (C1, the reference's own benchmark loop, C2, C4; C5 at N = 8), each with
+                its own clocks, roofline, parity and cpu_baseline (bench_extra.py)
 
 `--impl reference` times the reference's own CPU algorithm (the oracle; there is no JVM or FFTW in the image)
-on a bounded sample per step and prints the same line with "impl": "reference".
+on a bounded sample per step, with the same two-caller client, and prints the same line with "impl": "reference".
 """
 import argparse
 import ctypes
@@ -119,59 +128,108 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_fft_seconds(dims, reps):
+def base_config(n_gpus, extra=None):
+    """The workload both arms are labelled with (the reference arm must carry OUR config: same metric, same workload)."""
+    cfg = {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward)", "dims": list(DIMS),
+           "parallelism": "1 GPU" if n_gpus == 1 else "slab x%d over d0, exchange over NVLink" % n_gpus,
+           "l2": "inputs larger than L2 (2 GiB in + 2 GiB out vs 126 MB), no flush needed",
+           "client": "device-resident steps for `value`; two caller threads making synchronous provider calls for `e2e`"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def cpu_fft_seconds(dims, reps, callers=1):
+    """Best wall time of `callers` concurrent forward transforms of `dims` (each on its own array, one thread each: the
+    reference's FFT is single-threaded; ctypes releases the GIL)."""
     import numpy as np
     import oracle
     rng = np.random.default_rng(SEED)
     n = int(np.prod(dims))
-    x = rng.uniform(-0.5, 0.5, 2 * n)
+    xs = [rng.uniform(-0.5, 0.5, 2 * n) for _ in range(callers)]
     best = float("inf")
     for _ in range(reps):
+        th = [threading.Thread(target=oracle.fft, args=(list(dims), x)) for x in xs]
         t0 = time.perf_counter()
-        oracle.fft(list(dims), x)
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
         best = min(best, time.perf_counter() - t0)
     return best
 
 
 def cpu_baseline(sample=(256, 256, 256)):
-    """Bounded sample of the same workload: one forward c2c of a `sample` cube after a 64^3 warm-up."""
+    """Bounded sample of the same workload: one forward c2c of a `sample` cube after a 64^3 warm-up; then as many
+    independent transforms at once as the host has cores (bounded by memory: 1 GiB per 256^3 transform)."""
     cpu_fft_seconds((64, 64, 64), 1)
     secs = cpu_fft_seconds(sample, 1)
     n = sample[0] * sample[1] * sample[2]
+    cores = os.cpu_count() or 1
+    many = max(1, min(cores, 16))
+    secs_many = cpu_fft_seconds(sample, 1, callers=many)
     return {"value": fft_flops(n) / secs / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-            "host_cores": os.cpu_count(), "cpu_model": cpu_model(), "seconds": secs,
+            "host_cores": cores, "cpu_model": cpu_model(), "seconds": secs,
+            "all_cores": {"value": many * fft_flops(n) / secs_many / 1e9, "unit": "GFLOP/s", "cores": many,
+                          "note": "%d independent transforms at once, one thread each (the reference has no threaded FFT)" % many},
             "sample": "forward c2c %dx%dx%d (1/%d of the 512^3 points), oracle/fftops_oracle.c = C restatement of "
                       "FftOps.java, gcc -O2, 1 thread (the reference path is single-threaded)" %
                       (sample + ((DIMS[0] * DIMS[1] * DIMS[2]) // n,))}
+
+
+REFERENCE_CALLERS = 2  # the same client as our e2e leg: two caller threads, each making synchronous provider calls
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # keep (K + W) steps within a few minutes: 256^3 costs ~7 s per step, 128^3 ~0.8 s
-    sample = (256, 256, 256) if (args.steps + args.warmup) <= 12 else (128, 128, 128)
+    # 256^3 costs ~2.6 s per step on this pool's hosts (25 steps ~ 1 min); 512^3 would be ~25 s per step and 8 GiB per
+    # caller, so the step is a 1/8 sample of the workload -- GFLOP/s normalises the size (and the smaller cube fits the
+    # CPU's caches better, so the sample flatters the reference if anything)
+    sample = (256, 256, 256)
     import numpy as np
     import oracle
     n = sample[0] * sample[1] * sample[2]
-    x = np.random.default_rng(SEED).uniform(-0.5, 0.5, 2 * n)
-    for _ in range(args.warmup):
-        oracle.fft(list(sample), x)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.fft(list(sample), x)
-    secs = (time.perf_counter() - t0) / max(1, args.steps)
+    rng = np.random.default_rng(SEED)
+    xs = [rng.uniform(-0.5, 0.5, 2 * n) for _ in range(REFERENCE_CALLERS)]
+
+    def caller(x, steps):
+        for _ in range(steps):
+            oracle.fft(list(sample), x)
+
+    def run(steps):
+        th = [threading.Thread(target=caller, args=(x, steps)) for x in xs]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    # K steps in total, shared by the callers (rounded up to a whole number per caller)
+    per_caller = max(1, -(-args.steps // REFERENCE_CALLERS))
+    if args.warmup:
+        run(max(1, -(-args.warmup // REFERENCE_CALLERS)))
+    wall = run(per_caller)
+    transforms = per_caller * REFERENCE_CALLERS
+    secs = wall / transforms
     value = fft_flops(n) / secs / 1e9
-    desc = ("forward c2c %dx%dx%d per step, oracle/fftops_oracle.c (C restatement of the reference's FftOps.java; "
-            "no JVM/FFTW in the image), 1 thread: the reference path is single-threaded" % sample)
+    single = cpu_fft_seconds(sample, 1)
+    desc = ("forward c2c %dx%dx%d per step (1/8 of the 512^3 points), oracle/fftops_oracle.c (C restatement of the "
+            "reference's FftOps.java; no JVM/FFTW in the image); %d caller threads, one single-threaded transform each "
+            "-- the reference has no threaded FFT" % (sample + (REFERENCE_CALLERS,)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward)", "sample": desc},
-        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": desc,
-                         "host_cores": os.cpu_count(), "cpu_model": cpu_model()},
-        "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": base_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": REFERENCE_CALLERS, "kind": "port", "sample": desc,
+                         "host_cores": os.cpu_count(), "cpu_model": cpu_model(),
+                         "single_caller": {"value": fft_flops(n) / single / 1e9, "unit": "GFLOP/s", "cores": 1,
+                                           "ms_per_step": single * 1e3}},
+        "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "callers": REFERENCE_CALLERS},
     }))
 
 
@@ -243,19 +301,21 @@ def run_ours(args):
             plan.execute(x.data_ptr(), y.data_ptr(), stream)
 
         launches_per_step = plan.launches
-        parallelism = "1 GPU"
+        schedule = ("z in->out, y out->workspace (transposed store), x workspace->out" if plan.workspace_bytes
+                    else "one pass per axis, in place after the first")
     else:
         from shared_b200.sharded import SlabFft3d
         slab = SlabFft3d(DIMS, exchange=args.exchange, device=local, groups=args.groups,
-                         exchange_ctas=args.exchange_ctas)
-        if args.exchange == "pipe" and not args.no_graph:
-            slab.capture(x)
+                         exchange_ctas=args.exchange_ctas, chunks=args.chunks, bulk_store=args.bulk_store,
+                         graph=0 if args.no_graph else None)
+        if args.exchange == "pipe":
+            slab.capture(x)  # two eager steps; the C side replays recorded CUDA graphs from the third call on
 
         def step():
             slab.forward(x)
 
         launches_per_step = None  # counted below from the library's launch counter
-        parallelism = "slab x%d over d0, %s exchange over NVLink" % (world, args.exchange)
+        schedule = "%s exchange: y pass, z pass storing lines into the peers' slabs in groups, barrier, x pass per group" % args.exchange
 
     for _ in range(W):
         step()
@@ -370,42 +430,37 @@ def run_ours(args):
                                          "measured all-to-all rate of this box: ~590 GB/s per GPU (DESIGN.md 3.4)"}}
     t_load1 = time.time()
 
-    # ---- e2e: host arrays in pinned memory, H2D + kernels + D2H inside the timed region ------------------
-    e2e_steps = max(1, min(K, 5))
+    # ---- parity of the step that was timed (N > 1): outside the timed region --------------------------------------
+    parity = None
+    if world > 1:
+        parity = sharded_parity(torch, dist, shared_b200, slab, x, dev, rank, world, local, stream)
+
+    # ---- e2e: host arrays, H2D + kernels + D2H inside the timed region -------------------------------------------
+    e2e_steps = max(2, min(K, 6))
     if world == 1:
-        h_in, p_in = pinned_array(2 * n)
-        h_out, p_out = pinned_array(2 * n)
-        h_in[:] = 0.25
-        svc = shared_b200.CudaFftService(local)
-        svc.fft(DIMS, h_in, h_out)  # warm-up (plan + staging buffers)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            svc.fft(DIMS, h_in, h_out)
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        h2d = d2h = 16 * n
-        checksum = float(h_out[0])
-        assert abs(checksum - 0.25 * n) < 1e-6 * n, checksum
+        e2e = e2e_single_gpu(shared_b200, lib, local, n, flops, e2e_steps)
     else:
-        h_in, p_in = pinned_array(2 * n_local)
-        h_out, p_out = pinned_array(2 * n_local)
-        h_in[:] = 0.25
+        e2e = e2e_sharded(torch, dist, lib, slab, x, dev, n, n_local, flops, stream, e2e_steps)
 
-        def e2e_step():
-            lib.sstc_h2d(ctypes.c_void_p(x.data_ptr()), p_in, 16 * n_local, ctypes.c_void_p(stream))
-            out = slab.forward(x)
-            lib.sstc_d2h(p_out, ctypes.c_void_p(out.data_ptr()), 16 * n_local, ctypes.c_void_p(stream))
-            torch.cuda.synchronize()
-
-        e2e_step()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        dist.barrier()
-        t = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
-        h2d = d2h = 16 * n  # summed over ranks
+    # ---- the other BASELINE configs -------------------------------------------------------------------------------
+    extra = None
+    t_extra0 = time.time()
+    if not args.no_extra:
+        import bench_extra
+        if world == 1:
+            del x, y
+            torch.cuda.empty_cache()
+            extra = bench_extra.run_single_gpu(torch, shared_b200, peak, sampler, not args.no_cpu,
+                                               only=args.extra.split(",") if args.extra else None)
+        elif world == 8:
+            from shared_b200.sharded import SlabFft3d
+            slab.close()
+            del x
+            torch.cuda.empty_cache()
+            try:
+                extra = [bench_extra.config_c5(torch, dist, SlabFft3d, [1024, 1024, 1024], dev, rank, world, sampler)]
+            except Exception as e:  # noqa: BLE001
+                extra = [{"config": "C5", "error": "%s: %s" % (type(e).__name__, e)}]
     if sampler:
         sampler.stop()
 
@@ -414,27 +469,171 @@ def run_ours(args):
             "metric": METRIC, "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward), device-resident",
-                       "dims": list(DIMS), "parallelism": parallelism,
-                       "l2": "inputs larger than L2 (2 GiB in + 2 GiB out vs 126 MB), no flush needed",
-                       "schedule": ("z in->out, y out->workspace (transposed store), x workspace->out"
-                                    if world == 1 and plan.workspace_bytes else "one pass per axis, in place after the first")},
+            "config": base_config(world, {"schedule": schedule}),
             "hbm_model_gbs": 3 * 32.0 * n / ms_step / 1e6,
             "gpu_launches": int(launches), "launches_per_step": launches_per_step,
-            "e2e": {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                    "api": "CudaFftService.fft -> sstc_fft (host tier)" if world == 1 else
-                           "sstc_h2d + SlabFft3d.forward + sstc_d2h per rank"},
+            "e2e": e2e,
             "clocks": sampler.summary(t_wall0, t_load1) if sampler else None,
         }
         if roofline:
             line["roofline"] = roofline
+        if parity:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
+        if extra is not None:
+            line["extra_configs"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def sharded_parity(torch, dist, shared_b200, slab, x, dev, rank, world, local, stream):
+    """The timed step is the recorded CUDA-graph replay of the pipelined schedule: run it once more on the bench input,
+    gather input and output on rank 0, and compare with the 1-GPU plan on the same data; then the inverse."""
+    import math
+    n = DIMS[0] * DIMS[1] * DIMS[2]
+    replayed = slab.graph_count() if hasattr(slab, "graph_count") else None
+    out = slab.forward(x)
+    spec = out.clone()
+    back = slab.inverse(spec)
+    rt = torch.tensor([((back - x) ** 2).sum().item(), (x * x).sum().item()], dtype=torch.float64, device=dev)
+    dist.all_reduce(rt)
+    roundtrip = math.sqrt(rt[0].item() / rt[1].item())
+    xs = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
+    ys = [torch.empty_like(spec) for _ in range(world)] if rank == 0 else None
+    dist.gather(x, xs, dst=0)
+    dist.gather(spec, ys, dst=0)
+    res = None
+    if rank == 0:
+        from shared_b200.sharded import gather_transposed
+        full = torch.cat(xs)
+        del xs
+        got = gather_transposed(ys, DIMS).reshape(n, 2)
+        del ys
+        ref = torch.empty_like(full)
+        plan = shared_b200.FftPlan(shared_b200.FORWARD, DIMS, device=local)
+        plan.execute(full.data_ptr(), ref.data_ptr(), stream)
+        torch.cuda.synchronize()
+        err = (torch.linalg.norm(got - ref) / torch.linalg.norm(ref)).item()
+        res = {"what": "the CUDA-graph replay of the pipelined slab schedule (the timed step) against the 1-GPU plan on the "
+                       "gathered bench input; forward -> inverse round trip over all ranks",
+               "rel_l2_vs_1gpu": err, "bit_identical": bool(torch.equal(got, ref)),
+               "roundtrip_rel_l2": roundtrip, "tolerance": 1e-12 * math.log2(n),
+               "ok": bool(err < 1e-12 * math.log2(n) and roundtrip < 1e-12 * math.log2(n)),
+               "recorded_graphs": replayed,
+               "note": "not bit-identical by construction: the pipelined schedule transforms y before z, the 1-GPU plan z "
+                       "before y (same butterflies, different rounding order)"}
+        del full, got, ref
+        plan.close()
+        torch.cuda.empty_cache()
+    dist.barrier()
+    return res
+
+
+def e2e_single_gpu(shared_b200, lib, local, n, flops, steps):
+    """sstc_fft through CudaFftService.fft: single caller and two callers, pinned and pageable arrays."""
+    import numpy as np
+    svc = shared_b200.CudaFftService(local)
+
+    def run(arrays, callers, reps):
+        def caller(i):
+            for _ in range(reps):
+                svc.fft(DIMS, arrays[i][0], arrays[i][1])
+        th = [threading.Thread(target=caller, args=(i,)) for i in range(callers)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return (time.perf_counter() - t0) / (reps * callers)
+
+    def check(arrays):
+        for h_in, h_out in arrays:
+            assert abs(float(h_out[0]) - 0.25 * n) < 1e-6 * n and abs(float(h_out[1])) < 1e-6 * n, (h_out[0], h_out[1])
+            assert float(np.abs(h_out[2:4096]).max()) < 1e-6 * n
+
+    res = {}
+    pins = []
+    for _ in range(2):
+        h_in, p_in = pinned_array(2 * n)
+        h_out, p_out = pinned_array(2 * n)
+        h_in[0::2] = 0.25
+        h_in[1::2] = 0.0
+        pins.append((h_in, h_out, p_in, p_out))
+    arrays = [(a, b) for (a, b, _, _) in pins]
+    run(arrays, 2, 1)  # warm-up: plans, slots, device buffers
+    single = run(arrays, 1, steps)
+    double = run(arrays, 2, max(1, steps // 2 + 1))
+    check(arrays)
+    for (_, _, p_in, p_out) in pins:
+        lib.sstc_host_free(p_in)
+        lib.sstc_host_free(p_out)
+    del pins, arrays
+    pages = []
+    for _ in range(2):
+        h_in = np.empty(2 * n)
+        h_in[0::2] = 0.25
+        h_in[1::2] = 0.0
+        pages.append((h_in, np.zeros(2 * n)))
+    run(pages, 2, 1)  # warm-up: staging rings, copy threads
+    p_single = run(pages, 1, max(2, steps // 2))
+    p_double = run(pages, 2, max(1, steps // 2))
+    check(pages)
+    h2d = d2h = 16 * n
+    res = {"value": flops / double / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": double * 1e3, "steps": steps, "callers": 2, "host_memory": "pinned",
+           "api": "CudaFftService.fft -> sstc_fft (host tier), two caller threads, each call synchronous",
+           "single_caller": {"ms_per_step": single * 1e3, "value": flops / single / 1e9, "unit": "GFLOP/s",
+                             "bound": "one transform cannot finish before H2D + D2H: every output depends on every input"},
+           "pageable": {"two_callers_ms_per_step": p_double * 1e3, "two_callers_value": flops / p_double / 1e9,
+                        "single_caller_ms_per_step": p_single * 1e3, "single_caller_value": flops / p_single / 1e9,
+                        "unit": "GFLOP/s", "note": "plain numpy arrays = what GetPrimitiveArrayCritical hands the JNI glue; "
+                        "staged through the pinned ring by the copy threads"}}
+    return res
+
+
+def e2e_sharded(torch, dist, lib, slab, x, dev, n, n_local, flops, stream, steps):
+    """Per rank: H2D of its slab from pinned memory, the sharded forward, D2H of its result slab; max over ranks."""
+    h_in, p_in = pinned_array(2 * n_local)
+    h_out, p_out = pinned_array(2 * n_local)
+    h_in[:] = 0.25
+    s = ctypes.c_void_p(stream)
+
+    def h2d():
+        lib.sstc_h2d(ctypes.c_void_p(x.data_ptr()), p_in, 16 * n_local, s)
+
+    def e2e_step():
+        h2d()
+        out = slab.forward(x)
+        lib.sstc_d2h(p_out, ctypes.c_void_p(out.data_ptr()), 16 * n_local, s)
+        torch.cuda.synchronize()
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+            torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    e2e_s = timed(e2e_step, steps)
+    h2d_s = timed(h2d, steps)  # all ranks copying at once: what the host's PCIe fabric gives N links together
+    world = dist.get_world_size()
+    lib.sstc_host_free(p_in)
+    lib.sstc_host_free(p_out)
+    return {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
+            "ms_per_step": e2e_s * 1e3, "steps": steps, "callers": 1, "host_memory": "pinned",
+            "api": "sstc_h2d + SlabFft3d.forward (sstc_slab_forward) + sstc_d2h per rank",
+            "h2d_alone": {"ms": h2d_s * 1e3, "gbs_per_gpu": 16 * n_local / h2d_s / 1e9,
+                          "gbs_all_gpus": 16 * n / h2d_s / 1e9,
+                          "note": "all %d ranks copying their slab at the same time" % world}}
 
 
 def main():
@@ -449,7 +648,12 @@ def main():
     ap.add_argument("--groups", type=int, default=None, help="pipeline groups of the pipe exchange")
     ap.add_argument("--transposed-passes", type=int, default=None, dest="transposed_passes",
                     help="plan hint: -1 auto (default), 0 never, 1 always")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunks", type=int, default=None, help="pieces of the local pass in front of the exchange")
+    ap.add_argument("--bulk-store", type=int, default=None, dest="bulk_store",
+                    help="1: the exchange pass sends every line as one cp.async.bulk copy")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extra", action="store_true", dest="no_extra", help="skip extra_configs")
+    ap.add_argument("--extra", default=None, help="comma-separated subset of extra configs (c1,c1b,c2,c4)")
     ap.add_argument("--no-graph", action="store_true", dest="no_graph", help="issue the pipe schedule eagerly")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

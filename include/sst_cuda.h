@@ -142,6 +142,12 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
         int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas,
         void *stream);
 
+/* The same with the store variant selectable: bulk = 1 puts every transformed line back into shared memory and sends it
+ * as one bulk asynchronous copy (cp.async.bulk shared -> global) instead of per-thread 16-byte stores. */
+int sstc_fft_lines_scatter_ex_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes,
+        int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas, int bulk,
+        void *stream);
+
 /* The mirrored line scatter, for the inverse slab transform. The input is (nblocks, block_planes, plane_lines, len):
  * block q holds the planes that belong to rank q. The call transforms every line of planes [first, first + group) of
  * every block and stores line yl of plane xl of block q at d_out_blocks[q] + (xl*dst_plane_lines + yl)*len, i.e.
@@ -181,6 +187,10 @@ int sstc_slab_inverse(sstc_slab slab, const double *d_in, double **d_out, void *
  * issue eagerly). Setting an option drops the recorded graphs. */
 int sstc_slab_set_option(sstc_slab slab, const char *name, int64_t value);
 int64_t sstc_slab_graph_count(sstc_slab slab);
+/* Diagnostics: with option "trace" = 1 steps are issued eagerly with a timing event behind every launch; after a
+ * synchronise this writes "label<TAB>ms since the step's start<NEWLINE>" records into buf (at most max bytes) and
+ * returns the bytes written. tools/trace_sharded.py prints the timeline of one step on every rank. */
+int64_t sstc_slab_trace(sstc_slab slab, char *buf, int64_t max);
 int sstc_slab_destroy(sstc_slab slab);
 
 /* The same transform driven from ONE process over `ndev` devices (devices == NULL: 0..ndev-1): the library allocates
@@ -205,6 +215,15 @@ int sstc_fft3d_sharded_destroy(sstc_fft3d_sharded plan);
  * peer stores issued by earlier kernels on `stream` are complete before the flag is published, and kernels
  * after it start only when every rank has published `epoch`. */
 int sstc_peer_barrier_dev(void *const *d_flag_arrays, int nranks, int rank, uint64_t epoch, void *stream);
+
+/* Diagnostics (tools/exp_nvlink.py): copies `bytes` from src to dst (either may be a peer's memory) with `ctas` CTAs.
+ * mode 0: per-thread 16-byte loads and stores (the exchange pass's pattern); mode 1: bulk asynchronous copies through
+ * shared memory in pieces of `piece` bytes (cp.async.bulk in, cp.async.bulk out). Not used by any transform. */
+int sstc_exp_peer_copy(void *dst, const void *src, int64_t bytes, int mode, int piece, int ctas, void *stream);
+
+/* Diagnostics knob for tools/exp_overlap.py: "exchange_smem_kb" = dynamic shared memory the pipelined exchange kernel
+ * requests (beyond its need), which keeps other kernels' CTAs off its SMs. */
+int sstc_exp_set(const char *name, int64_t value);
 
 /* Cross-process device-memory sharing for the one-process-per-GPU layout (cudaIpc*): export a 64-byte
  * handle for a buffer from sstc_malloc, open a peer's handle, close it. */

@@ -56,6 +56,9 @@ SIGNATURES = {
     "sstc_fft_lines_scatter_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int64,
                                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
+    "sstc_fft_lines_scatter_ex_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int64,
+                                                     ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                     ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     "sstc_fft_planes_scatter_dev": (ctypes.c_int, [ctypes.c_void_p, c_void_pp, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
                                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                    ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
@@ -63,6 +66,7 @@ SIGNATURES = {
     "sstc_slab_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
     "sstc_slab_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
     "sstc_slab_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "sstc_slab_trace": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "sstc_slab_graph_count": (ctypes.c_int64, [ctypes.c_void_p]),
     "sstc_slab_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "sstc_fft3d_sharded_create": (ctypes.c_int, [c_void_pp, c_i32_p, ctypes.c_int, c_i32_p]),
@@ -73,6 +77,9 @@ SIGNATURES = {
     "sstc_fft3d_sharded_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "sstc_fft3d_sharded_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "sstc_peer_barrier_dev": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p]),
+    "sstc_exp_peer_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p]),
+    "sstc_exp_set": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "sstc_ipc_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "sstc_ipc_open": (ctypes.c_int, [ctypes.c_char_p, c_void_pp]),
     "sstc_ipc_close": (ctypes.c_int, [ctypes.c_void_p]),

@@ -468,6 +468,141 @@ fft_pow2_kernel(const FftPassArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The exchange pass of the slab transform as a software-pipelined persistent kernel (line scatter only, see
+// FftPassArgs::ls_*): one elected thread per CTA drives the SM's bulk-copy unit -- cp.async.bulk global -> shared for
+// the NEXT tile's lines (completion on an mbarrier) and cp.async.bulk shared -> global for the PREVIOUS tile's
+// transformed lines (into the peers' memory over NVLink) -- while all threads run the butterflies of the CURRENT
+// tile. Three tile buffers rotate: a buffer is, in turn, the landing zone of the bulk load (dense lines), the
+// exchange area of the Stockham stages (padded lines), and the source of the bulk stores (dense lines again).
+// With loads and stores off the threads' critical path the pass is bound by the link, not by the latency of one
+// tile's load -> compute -> store chain, which is what it degrades to (500 instead of 690 GB/s, measured on 8 B200)
+// when the x pass of the previous group shares the SMs and HBM with it.
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int C>
+struct ExchangeTile {
+    static constexpr int T = L / 8;
+    static constexpr int THREADS = C * T;
+    static constexpr int LINE = fft_pad(L);
+    static constexpr int BUF_ELEMS = LINE * C;       // padded: the stages' layout is the larger one
+    static constexpr int NBUF = 3;
+    static constexpr int SMEM_BYTES = NBUF * BUF_ELEMS * 16 + 64;  // + the mbarriers
+};
+
+// source line and destination of line number `line` of this launch (the addressing of fft_pow2_tile's line scatter)
+__device__ __forceinline__ void exchange_line(const FftPassArgs &a, int L, int64_t line, const double2 *&src, double2 *&dst) {
+    if (a.ls_sub > 0) {
+        const int64_t yl = line % a.ls_sub, t1 = line / a.ls_sub;
+        const int q = (int) (t1 % a.ls_nblk);
+        const int64_t xl = a.ls_first + t1 / a.ls_nblk;
+        src = a.in + (((int64_t) q * a.ls_block_lines + xl) * a.ls_sub + yl) * L;
+        dst = a.blk[q] + (xl * a.ls_plane_lines + yl) * L;
+    } else {
+        const int64_t yq = line % a.ls_group, t1 = line / a.ls_group;
+        const int q = (int) (t1 % a.ls_nblk);
+        const int64_t xl = t1 / a.ls_nblk;
+        const int64_t yl = a.ls_first + yq;
+        src = a.in + (xl * a.ls_plane_lines + (int64_t) q * a.ls_block_lines + yl) * L;
+        dst = a.blk[q] + (xl * a.ls_block_lines + yl) * L;
+    }
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    }
+}
+
+template <int L, int C>
+__global__ void __launch_bounds__(ExchangeTile<L, C>::THREADS, 2) fft_exchange_kernel(const FftPassArgs a) {
+    using Tile = ExchangeTile<L, C>;
+    constexpr int T = Tile::T;
+    extern __shared__ __align__(128) double2 sm[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + Tile::NBUF * Tile::BUF_ELEMS);
+    const int tid = threadIdx.x, t = tid % T, c = tid / T;
+    const int64_t ntiles = a.ntiles;
+
+    // thread 0: arm the buffer's mbarrier and pull the C lines of tile `tile` into buffer `b`
+    auto issue_load = [&](int64_t tile, int b) {
+        const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&bars[b]);
+        const int64_t first = tile * C;
+        const int nl = (int) (a.outer - first < C ? a.outer - first : C);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (nl * L * 16)) : "memory");
+        for (int k = 0; k < nl; k++) {
+            const double2 *src;
+            double2 *dst;
+            exchange_line(a, L, first + k, src, dst);
+            const uint32_t sa = (uint32_t) __cvta_generic_to_shared(sm + b * Tile::BUF_ELEMS + k * L);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa),
+                         "l"(src), "r"((uint32_t) (L * 16)), "r"(bar)
+                         : "memory");
+        }
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < Tile::NBUF; b++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t) __cvta_generic_to_shared(&bars[b])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int64_t) blockIdx.x < ntiles) {
+            issue_load(blockIdx.x, 0);
+        }
+    }
+    __syncthreads();
+
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int b = (int) (it % Tile::NBUF);
+        double2 *buf = sm + b * Tile::BUF_ELEMS;
+        const int64_t line = tile * C + c;
+        const bool active = line < a.outer;
+        if (tid == 0 && tile + gridDim.x < ntiles) {
+            // the buffer the next tile lands in was the store source two tiles ago: all but the latest store group
+            // must have finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_load(tile + gridDim.x, (int) ((it + 1) % Tile::NBUF));
+        }
+        mbar_wait((uint32_t) __cvta_generic_to_shared(&bars[b]), (uint32_t) ((it / Tile::NBUF) & 1));
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const double2 z = active ? buf[c * L + t + m * T] : make_double2(0.0, 0.0);
+            v[m] = a.inverse ? make_double2(z.y, z.x) : z;
+        }
+        __syncthreads();  // the dense lines have been read: the buffer becomes the stages' (padded) exchange area
+        Pow2Stages<L, C, false, 1>::run(v, t, c, buf, a.tw);
+        __syncthreads();  // the last exchange has been read: the buffer becomes the stores' (dense) source
+        const double s = a.scale;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            buf[c * L + t + m * T] = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t first = tile * C;
+            const int nl = (int) (a.outer - first < C ? a.outer - first : C);
+            for (int k = 0; k < nl; k++) {
+                const double2 *src;
+                double2 *dst;
+                exchange_line(a, L, first + k, src, dst);
+                const uint32_t sa = (uint32_t) __cvta_generic_to_shared(buf + k * L);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sa),
+                             "r"((uint32_t) (L * 16))
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every line has been written before the CTA retires
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Real transforms of even power-of-two length N = 2H on the last axis, as ONE complex transform of length H
 // (the packing trick: z[j] = x[2j] + i x[2j+1], which is exactly how a real line reads when viewed as double2):
 //   r2c   Z = FFT_H(z);  X[k] = (Z[k] + conj Z[H-k])/2 - (i/2) w^k (Z[k] - conj Z[H-k]),  w = e^{-2 pi i/N},

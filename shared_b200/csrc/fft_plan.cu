@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -240,6 +241,49 @@ static void dispatch_real(FftPassArgs &a, int N, cudaStream_t stream) {
     case 2048: launch_real<2048>(a, stream); break;
     case 4096: launch_real<4096>(a, stream); break;
     default: throw std::runtime_error("internal: real transform length");
+    }
+}
+
+// Diagnostics (sstc_exp_set "exchange_smem_kb"): dynamic shared memory requested by the exchange kernels beyond what they
+// use, to keep other kernels' CTAs off the SMs they run on (tools/exp_overlap.py).
+static std::atomic<int64_t> g_exchange_smem_kb{0};
+
+// The software-pipelined exchange pass (fft_exchange_kernel): persistent grid, at most `grid_limit` CTAs (default: two
+// per SM, what its three tile buffers allow at L = 512).
+template <int L>
+static void launch_exchange(const FftPassArgs &a0, cudaStream_t stream) {
+    constexpr int C = contig_lines(L);
+    using Tile = ExchangeTile<L, C>;
+    static std::once_flag once[16];
+    static int sms[16];
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 15], [dev] {
+        SSTC_CUDA(cudaFuncSetAttribute(fft_exchange_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SSTC_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+    });
+    const size_t smem = std::max<size_t>(Tile::SMEM_BYTES, std::min<size_t>(227, (size_t) g_exchange_smem_kb.load()) * 1024);
+    FftPassArgs a = a0;
+    a.ntiles = (a.outer + C - 1) / C;
+    int64_t grid = a.grid_limit > 0 ? a.grid_limit : 2 * (int64_t) sms[dev & 15];
+    grid = std::max<int64_t>(1, std::min(grid, a.ntiles));
+    fft_exchange_kernel<L, C><<<(unsigned) grid, Tile::THREADS, smem, stream>>>(a);
+    check_launch("fft_exchange_kernel");
+}
+
+static void dispatch_exchange(const FftPassArgs &a, int L, cudaStream_t stream) {
+    switch (L) {
+    case 8: launch_exchange<8>(a, stream); break;
+    case 16: launch_exchange<16>(a, stream); break;
+    case 32: launch_exchange<32>(a, stream); break;
+    case 64: launch_exchange<64>(a, stream); break;
+    case 128: launch_exchange<128>(a, stream); break;
+    case 256: launch_exchange<256>(a, stream); break;
+    case 512: launch_exchange<512>(a, stream); break;
+    case 1024: launch_exchange<1024>(a, stream); break;
+    case 2048: launch_exchange<2048>(a, stream); break;
+    case 4096: launch_exchange<4096>(a, stream); break;
+    default: throw std::runtime_error("internal: exchange length");
     }
 }
 
@@ -854,7 +898,16 @@ static void scatter_common(FftPassArgs &a, const double *d_in, void *const *d_ou
     }
     a.ls_nblk = nblocks;
     a.grid_limit = max_ctas > 0 ? max_ctas : 0;
-    a.ls_bulk = bulk ? 1 : 0;
+    a.ls_bulk = bulk == 1 ? 1 : 0;
+}
+
+// bulk: 0 = per-thread stores, 1 = bulk stores from the tile kernel, 2 = the software-pipelined exchange kernel
+static void dispatch_scatter(const FftPassArgs &a, int len, int bulk, cudaStream_t stream) {
+    if (bulk == 2) {
+        dispatch_exchange(a, len, stream);
+    } else {
+        dispatch_axis(a, len, false, stream);
+    }
 }
 
 void fft_lines_scatter(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes, int32_t plane_lines,
@@ -873,7 +926,7 @@ void fft_lines_scatter(const double *d_in, void *const *d_out_blocks, int nblock
     a.ls_first = first;
     a.ls_block_lines = plane_lines / nblocks;
     a.ls_plane_lines = plane_lines;
-    dispatch_axis(a, len, false, stream);
+    dispatch_scatter(a, len, bulk, stream);
 }
 
 void fft_planes_scatter(const double *d_in, void *const *d_out_blocks, int nblocks, int32_t block_planes, int32_t plane_lines,
@@ -891,7 +944,7 @@ void fft_planes_scatter(const double *d_in, void *const *d_out_blocks, int nbloc
     a.ls_block_lines = block_planes;
     a.ls_plane_lines = dst_plane_lines;
     a.ls_sub = plane_lines;
-    dispatch_axis(a, len, false, stream);
+    dispatch_scatter(a, len, bulk, stream);
 }
 
 }  // namespace sstc
@@ -1004,6 +1057,25 @@ int sstc_fft_lines_scatter_dev(const double *d_in, void *const *d_out_blocks, in
         void *stream) {
     return guarded([&] {
         fft_lines_scatter(d_in, d_out_blocks, nblocks, planes, plane_lines, len, first, group, inverse, scale, max_ctas, 0,
+                as_stream(stream));
+    });
+}
+
+int sstc_exp_set(const char *name, int64_t value) {
+    return guarded([&] {
+        if (name && std::string(name) == "exchange_smem_kb") {
+            g_exchange_smem_kb.store(value);
+        } else {
+            throw std::runtime_error("Unknown option");
+        }
+    });
+}
+
+int sstc_fft_lines_scatter_ex_dev(const double *d_in, void *const *d_out_blocks, int nblocks, int64_t planes,
+        int32_t plane_lines, int32_t len, int32_t first, int32_t group, int inverse, double scale, int64_t max_ctas, int bulk,
+        void *stream) {
+    return guarded([&] {
+        fft_lines_scatter(d_in, d_out_blocks, nblocks, planes, plane_lines, len, first, group, inverse, scale, max_ctas, bulk,
                 as_stream(stream));
     });
 }

@@ -21,8 +21,10 @@
 #include <string.h>
 
 #include <map>
+#include <algorithm>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <tuple>
 #include <vector>
 
@@ -39,10 +41,16 @@ struct sstc_slab_s {
     std::vector<cudaEvent_t> events;
     size_t next_event = 0;
     int groups = 4, chunks = 1, exchange_ctas = 0, bulk = 0, use_graph = 1;
+    int order = 0, head_ctas = 0;  // see issue_forward
     uint64_t step = 0;
     std::map<std::tuple<int, const void *, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, const void *, int>, int64_t> graph_kernels;
     std::map<std::pair<int, const void *>, int> seen;
+    // diagnostics ("trace" option): timing events behind every launch of an eagerly issued step
+    int trace = 0;
+    std::vector<cudaEvent_t> marks;
+    std::vector<std::string> mark_labels;
+    size_t next_mark = 0;
 };
 
 namespace sstc {
@@ -62,6 +70,21 @@ static cudaEvent_t record_on(sstc_slab_s &S, cudaStream_t s) {
     return e;
 }
 
+// trace: a timing event on stream s, labelled
+static void mark(sstc_slab_s &S, cudaStream_t s, const std::string &label) {
+    if (!S.trace) {
+        return;
+    }
+    if (S.next_mark == S.marks.size()) {
+        cudaEvent_t e;
+        SSTC_CUDA(cudaEventCreate(&e));
+        S.marks.push_back(e);
+        S.mark_labels.push_back(label);
+    }
+    S.mark_labels[S.next_mark] = label;
+    SSTC_CUDA(cudaEventRecord(S.marks[S.next_mark++], s));
+}
+
 static int pick_divisor(int want, int of) {
     for (int g : {want, 4, 2, 1}) {
         if (g >= 1 && of % g == 0) {
@@ -71,14 +94,26 @@ static int pick_divisor(int want, int of) {
     return 1;
 }
 
-// barrier on s_bar behind `after`; the event it returns fires when every rank has passed it
-static cudaEvent_t barrier_after(sstc_slab_s &S, cudaEvent_t after) {
-    SSTC_CUDA(cudaStreamWaitEvent(S.s_bar, after, 0));
-    launch_peer_barrier(S.flags, S.nranks, S.rank, 0, S.s_bar);
+// Cross-rank barrier behind the exchange kernel just issued on s_z; the event it returns fires when every rank has
+// passed it. The signal is issued on s_z itself, so that it leaves ahead of the next exchange kernel's data; the wait
+// runs on the high-priority side stream.
+static cudaEvent_t barrier_after_exchange(sstc_slab_s &S) {
+    launch_peer_signal(S.flags, S.nranks, S.rank, S.s_z);
+    SSTC_CUDA(cudaStreamWaitEvent(S.s_bar, record_on(S, S.s_z), 0));
+    launch_peer_wait(S.flags, S.nranks, S.rank, S.s_bar);
     return record_on(S, S.s_bar);
 }
 
 // The forward schedule on S.s_main (and the side streams, forked from and joined back into it).
+//
+// Tasks: Y(c) = the local y pass of plane chunk c; E(c, g) = the exchange (z pass + line scatter) of y group g of chunk
+// c, which needs Y(c); X(g) = the x pass of the received columns of group g, which needs E(c, g) of EVERY chunk on every
+// rank (one barrier). The link is the bottleneck, so the order of the E tasks decides what is exposed:
+//   order 0  E(*, 0) chunk by chunk behind the y pass, then E(all, g) for g = 1..: every x pass but the last runs beside
+//            the exchange, but the exchange of group 0 crawls behind the y pass (small launches that share the SMs);
+//   order 1  chunk-major first, group-major last: E(c, all groups) as ONE launch per chunk for c < C-1, uncapped (nothing
+//            needs the SMs yet but the next chunk's y pass), then the last chunk group by group with the x passes beside
+//            it. The link starts after 1/C of the y pass and never waits for a small launch.
 static void issue_forward(sstc_slab_s &S, const double *x, int parity) {
     const int P = S.nranks;
     const int G = pick_divisor(S.groups, S.y_loc), C = pick_divisor(S.chunks, S.x_loc);
@@ -89,36 +124,72 @@ static void issue_forward(sstc_slab_s &S, const double *x, int parity) {
     for (int q = 0; q < P; q++) {
         base[q] = static_cast<char *>(S.recv[parity][q]) + (size_t) S.rank * S.block * 16;
     }
-    // y pass, local, in C chunks of planes; group 0 of the exchange follows chunk by chunk
+    auto chunk_dst = [&](int c, void **dst) {
+        for (int q = 0; q < P; q++) {
+            dst[q] = static_cast<char *>(base[q]) + (size_t) c * xc * kstride * 16;
+        }
+    };
+    // y pass, local, in C chunks of planes
     std::vector<cudaEvent_t> y_done;
+    mark(S, S.s_main, "start");
     for (int c = 0; c < C; c++) {
         const size_t off = (size_t) c * xc * plane * 16;
         fft_axis_pass(reinterpret_cast<const char *>(x) + off, work + off, xc, S.d1, S.d2, PASS_C2C, 0, 1.0, S.s_main);
         y_done.push_back(record_on(S, S.s_main));
+        mark(S, S.s_main, "y" + std::to_string(c) + " done");
+    }
+    const bool two_phase = S.order == 1 && C > 1;
+    if (two_phase) {
+        for (int c = 0; c + 1 < C; c++) {
+            SSTC_CUDA(cudaStreamWaitEvent(S.s_z, y_done[(size_t) c], 0));
+            void *dst[8];
+            chunk_dst(c, dst);
+            mark(S, S.s_z, "E" + std::to_string(c) + ".* begin");
+            fft_lines_scatter(reinterpret_cast<const double *>(work + (size_t) c * xc * plane * 16), dst, P, xc, S.d1, S.d2, 0,
+                    S.y_loc, 0, 1.0, S.head_ctas, S.bulk, S.s_z);
+            mark(S, S.s_z, "E" + std::to_string(c) + ".* done");
+        }
     }
     cudaEvent_t joined = nullptr;
     for (int g = 0; g < G; g++) {
-        if (g == 0) {
+        if (two_phase) {
+            const int c = C - 1;
+            if (g == 0) {
+                SSTC_CUDA(cudaStreamWaitEvent(S.s_z, y_done[(size_t) c], 0));
+            }
+            void *dst[8];
+            chunk_dst(c, dst);
+            mark(S, S.s_z, "e" + std::to_string(g) + " begin");
+            fft_lines_scatter(reinterpret_cast<const double *>(work + (size_t) c * xc * plane * 16), dst, P, xc, S.d1, S.d2, g * yg,
+                    yg, 0, 1.0, S.exchange_ctas, S.bulk, S.s_z);
+            mark(S, S.s_z, "e" + std::to_string(g) + " done");
+        } else if (g == 0) {
             for (int c = 0; c < C; c++) {
                 SSTC_CUDA(cudaStreamWaitEvent(S.s_z, y_done[(size_t) c], 0));
                 void *dst[8];
-                for (int q = 0; q < P; q++) {
-                    dst[q] = static_cast<char *>(base[q]) + (size_t) c * xc * kstride * 16;
-                }
+                chunk_dst(c, dst);
+                mark(S, S.s_z, "e0." + std::to_string(c) + " begin");
                 fft_lines_scatter(reinterpret_cast<const double *>(work + (size_t) c * xc * plane * 16), dst, P, xc, S.d1, S.d2, 0,
                         yg, 0, 1.0, S.exchange_ctas, S.bulk, S.s_z);
+                mark(S, S.s_z, "e0." + std::to_string(c) + " done");
             }
         } else {
+            mark(S, S.s_z, "e" + std::to_string(g) + " begin");
             fft_lines_scatter(S.work, base, P, S.x_loc, S.d1, S.d2, g * yg, yg, 0, 1.0, S.exchange_ctas, S.bulk, S.s_z);
+            mark(S, S.s_z, "e" + std::to_string(g) + " done");
         }
-        cudaEvent_t arrived = barrier_after(S, record_on(S, S.s_z));
+        cudaEvent_t arrived = barrier_after_exchange(S);
+        mark(S, S.s_bar, "barrier" + std::to_string(g) + " passed");
         SSTC_CUDA(cudaStreamWaitEvent(S.s_x, arrived, 0));
         char *ptr = static_cast<char *>(S.recv[parity][S.rank]) + (size_t) g * cols * 16;
         const int64_t layout[4] = {0, kstride, 0, kstride};
+        mark(S, S.s_x, "x" + std::to_string(g) + " begin");
         fft_axis_pass(ptr, ptr, 1, S.d0, cols, PASS_C2C, 0, 1.0, S.s_x, layout);  // x on this group's columns
+        mark(S, S.s_x, "x" + std::to_string(g) + " done");
         joined = record_on(S, S.s_x);
     }
     SSTC_CUDA(cudaStreamWaitEvent(S.s_main, joined, 0));
+    mark(S, S.s_main, "end");
 }
 
 // The inverse schedule: x pass locally, the z pass scatters whole lines into the owners' natural slabs plane group by
@@ -137,7 +208,7 @@ static void issue_inverse(sstc_slab_s &S, const double *y, int parity) {
     cudaEvent_t joined = nullptr;
     for (int g = 0; g < G; g++) {
         fft_planes_scatter(S.work, base, P, S.x_loc, S.y_loc, S.d1, S.d2, g * xg, xg, 1, 1.0, S.exchange_ctas, S.bulk, S.s_z);
-        cudaEvent_t arrived = barrier_after(S, record_on(S, S.s_z));
+        cudaEvent_t arrived = barrier_after_exchange(S);
         SSTC_CUDA(cudaStreamWaitEvent(S.s_x, arrived, 0));
         char *ptr = static_cast<char *>(S.recv[parity][S.rank]) + (size_t) g * xg * plane * 16;
         fft_axis_pass(ptr, ptr, xg, S.d1, S.d2, PASS_C2C, 1, 1.0 / (double) S.n_total, S.s_x);
@@ -155,13 +226,14 @@ static void slab_run(sstc_slab_s &S, int dir, const double *in, double **out, cu
     const int parity = (int) (S.step & 1);
     S.step++;
     S.next_event = 0;
+    S.next_mark = 0;
     // the caller's stream joins in front of and behind the schedule, which lives on the context's own streams
     cudaEvent_t enter = slab_event(S);
     SSTC_CUDA(cudaEventRecord(enter, user));
     SSTC_CUDA(cudaStreamWaitEvent(S.s_main, enter, 0));
     const auto key = std::make_tuple(dir, (const void *) in, parity);
     auto it = S.graphs.find(key);
-    if (it == S.graphs.end() && S.use_graph && S.seen[std::make_pair(dir, (const void *) in)] >= 2) {
+    if (it == S.graphs.end() && S.use_graph && !S.trace && S.seen[std::make_pair(dir, (const void *) in)] >= 2) {
         // both parities have run eagerly with this input (attributes set, tables built): record this one
         cudaGraph_t graph = nullptr;
         const int64_t before = g_launch_count.load();
@@ -307,6 +379,7 @@ static sstc_slab_s *slab_create(const int32_t *dims, int nranks, int rank, void 
         }
         fft_lines_scatter(S->work, self, nranks, 1, S->d1, S->d2, 0, 1, 0, 1.0, 1, 0, S->s_main);
         fft_lines_scatter(S->work, self, nranks, 1, S->d1, S->d2, 0, 1, 0, 1.0, 1, 1, S->s_main);
+        fft_lines_scatter(S->work, self, nranks, 1, S->d1, S->d2, 0, 1, 0, 1.0, 1, 2, S->s_main);
     }
     const int64_t layout[4] = {0, 8, 0, 8};
     fft_axis_pass(S->work, S->work, 1, S->d0, 8, PASS_C2C, 0, 1.0, S->s_main, layout);
@@ -430,9 +503,18 @@ int sstc_slab_set_option(sstc_slab slab, const char *name, int64_t value) {
         } else if (n == "exchange_ctas") {
             slab->exchange_ctas = (int) value;
         } else if (n == "bulk_store") {
-            slab->bulk = value ? 1 : 0;
+            if (value > 2) {
+                throw std::runtime_error("Invalid option value");
+            }
+            slab->bulk = (int) value;
+        } else if (n == "order") {
+            slab->order = value ? 1 : 0;
+        } else if (n == "head_ctas") {
+            slab->head_ctas = (int) value;
         } else if (n == "graph") {
             slab->use_graph = value ? 1 : 0;
+        } else if (n == "trace") {
+            slab->trace = value ? 1 : 0;
         } else {
             throw std::runtime_error("Unknown option");
         }
@@ -447,6 +529,28 @@ int sstc_slab_set_option(sstc_slab slab, const char *name, int64_t value) {
         slab->graphs.clear();
         slab->graph_kernels.clear();
     });
+}
+
+// Diagnostics: after a step issued with the "trace" option (and a synchronise), writes up to `max` records of
+// "label<TAB>milliseconds since the step's start<NEWLINE>" into buf; returns the number of bytes written.
+int64_t sstc_slab_trace(sstc_slab slab, char *buf, int64_t max) {
+    int64_t used = 0;
+    guarded([&] {
+        if (!slab || !buf || slab->next_mark == 0) {
+            return;
+        }
+        DeviceGuard guard(slab->device);
+        std::string out;
+        for (size_t i = 0; i < slab->next_mark; i++) {
+            SSTC_CUDA(cudaEventSynchronize(slab->marks[i]));
+            float ms = 0;
+            SSTC_CUDA(cudaEventElapsedTime(&ms, slab->marks[0], slab->marks[i]));
+            out += slab->mark_labels[i] + "\t" + std::to_string(ms) + "\n";
+        }
+        used = std::min<int64_t>(max, (int64_t) out.size());
+        memcpy(buf, out.data(), (size_t) used);
+    });
+    return used;
 }
 
 int64_t sstc_slab_graph_count(sstc_slab slab) { return slab ? (int64_t) slab->graphs.size() : 0; }

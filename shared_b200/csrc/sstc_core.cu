@@ -142,6 +142,67 @@ __global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned 
     __threadfence_system();
 }
 
+// The same barrier in two halves, for schedules that keep the link busy: the SIGNAL goes out on the stream of the kernel
+// whose stores it publishes, i.e. in front of the next exchange kernel's data (measured on 8 B200: a flag written while
+// the next group's lines are already streaming queues behind tens of megabytes and arrives 50-80 us late); the WAIT
+// runs on a side stream. Slot 8 of a rank's own array counts its signals, slot 9 its waits.
+__global__ void peer_signal_kernel(PeerFlags f, int nranks, int rank) {
+    __shared__ unsigned long long next;
+    if (threadIdx.x == 0) {
+        next = ++f.ptr[rank][8];
+    }
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r >= nranks) {
+        return;
+    }
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(f.ptr[r] + rank) = next;
+}
+
+__global__ void peer_wait_kernel(PeerFlags f, int nranks, int rank, unsigned long long *err) {
+    __shared__ unsigned long long next;
+    if (threadIdx.x == 0) {
+        next = ++f.ptr[rank][9];
+    }
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r >= nranks) {
+        return;
+    }
+    const unsigned long long epoch = next;
+    volatile unsigned long long *local = f.ptr[rank] + r;
+    const long long start = clock64();
+    while (*local < epoch) {
+        if (clock64() - start > 8000000000LL) {
+            if (err) {
+                *reinterpret_cast<volatile unsigned long long *>(err) = (epoch << 16) | ((unsigned long long) rank << 8) | (unsigned long long) r;
+                __threadfence_system();
+            }
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+static PeerFlags peer_flags(void *const *flag_arrays, int nranks) {
+    PeerFlags f;
+    for (int r = 0; r < 8; r++) {
+        f.ptr[r] = r < nranks ? static_cast<unsigned long long *>(flag_arrays[r]) : nullptr;
+    }
+    return f;
+}
+
+void launch_peer_signal(void *const *flag_arrays, int nranks, int rank, cudaStream_t stream) {
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer_flags(flag_arrays, nranks), nranks, rank);
+    check_launch("peer_signal_kernel");
+}
+
+void launch_peer_wait(void *const *flag_arrays, int nranks, int rank, cudaStream_t stream) {
+    peer_wait_kernel<<<1, 32, 0, stream>>>(peer_flags(flag_arrays, nranks), nranks, rank, barrier_error_word());
+    check_launch("peer_wait_kernel");
+}
+
 void launch_peer_barrier(void *const *flag_arrays, int nranks, int rank, unsigned long long epoch, cudaStream_t stream) {
     PeerFlags f;
     for (int r = 0; r < 8; r++) {
@@ -303,3 +364,103 @@ int sstc_stream_sync(void *stream) {
 }
 
 }  // extern "C"
+
+// ---- diagnostics: what a kernel can push into a peer's memory over NVLink (tools/exp_nvlink.py) -----------------
+// mode 0: every thread loads and stores 16-byte pieces (8 in flight), the access pattern of the exchange pass;
+// mode 1: the CTA pulls `piece` bytes into shared memory with one bulk copy (cp.async.bulk global -> shared, mbarrier)
+//         and pushes them out with one bulk copy (shared -> global), two buffers in flight.
+namespace sstc {
+
+__global__ void __launch_bounds__(256) peer_copy_ldst_kernel(double2 *__restrict__ dst, const double2 *__restrict__ src, int64_t n) {
+    const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n; i += 8 * stride) {
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            v[m] = src[i + m * stride];
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            dst[i + m * stride] = v[m];
+        }
+    }
+    for (; i < n; i += stride) {
+        dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(32) peer_copy_bulk_kernel(char *dst, const char *src, int64_t bytes, int piece) {
+    extern __shared__ __align__(128) char smem[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    const int64_t npieces = bytes / piece;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; b++) {
+            const uint32_t ba = (uint32_t) __cvta_generic_to_shared(&bar[b]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ba));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint32_t phase[2] = {0, 0};
+        int64_t p = blockIdx.x;
+        int buf = 0;
+        // prologue: first load
+        if (p < npieces) {
+            const uint32_t ba = (uint32_t) __cvta_generic_to_shared(&bar[0]);
+            const uint32_t sa = (uint32_t) __cvta_generic_to_shared(smem);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t) piece) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa),
+                         "l"(src + p * piece), "r"((uint32_t) piece), "r"(ba)
+                         : "memory");
+        }
+        for (; p < npieces; p += gridDim.x, buf ^= 1) {
+            const int64_t next = p + gridDim.x;
+            if (next < npieces) {
+                // the other buffer's previous store must have read its source before it is overwritten
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const uint32_t ba = (uint32_t) __cvta_generic_to_shared(&bar[buf ^ 1]);
+                const uint32_t sa = (uint32_t) __cvta_generic_to_shared(smem + (size_t) (buf ^ 1) * piece);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t) piece) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa),
+                             "l"(src + next * piece), "r"((uint32_t) piece), "r"(ba)
+                             : "memory");
+            }
+            const uint32_t ba = (uint32_t) __cvta_generic_to_shared(&bar[buf]);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done)
+                             : "r"(ba), "r"(phase[buf])
+                             : "memory");
+            }
+            phase[buf] ^= 1;
+            const uint32_t sa = (uint32_t) __cvta_generic_to_shared(smem + (size_t) buf * piece);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + p * piece), "r"(sa),
+                         "r"((uint32_t) piece)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+}  // namespace sstc
+
+extern "C" int sstc_exp_peer_copy(void *dst, const void *src, int64_t bytes, int mode, int piece, int ctas, void *stream) {
+    return sstc::guarded([&] {
+        if (!dst || !src || bytes <= 0 || ctas <= 0 || (bytes & 15)) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        if (mode == 0) {
+            sstc::peer_copy_ldst_kernel<<<ctas, 256, 0, sstc::as_stream(stream)>>>(static_cast<double2 *>(dst),
+                    static_cast<const double2 *>(src), bytes / 16);
+        } else {
+            if (piece < 1024 || piece > 100 * 1024 || (piece & 127) || bytes % piece) {
+                throw std::runtime_error("Invalid piece size");
+            }
+            SSTC_CUDA(cudaFuncSetAttribute(sstc::peer_copy_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * piece));
+            sstc::peer_copy_bulk_kernel<<<ctas, 32, 2 * (size_t) piece, sstc::as_stream(stream)>>>(static_cast<char *>(dst),
+                    static_cast<const char *>(src), bytes, piece);
+        }
+        sstc::check_launch("peer_copy_kernel");
+    });
+}

@@ -67,6 +67,9 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 // The cross-GPU flag barrier (sstc_core.cu); epoch 0 = the kernel counts its own calls (graph-capturable).
 void launch_peer_barrier(void *const *flag_arrays, int nranks, int rank, unsigned long long epoch, cudaStream_t stream);
+// The barrier in two halves (a context uses either this pair or launch_peer_barrier, never both on one flag set).
+void launch_peer_signal(void *const *flag_arrays, int nranks, int rank, cudaStream_t stream);
+void launch_peer_wait(void *const *flag_arrays, int nranks, int rank, cudaStream_t stream);
 
 // Grow-only device scratch owned by the host tier (one per thread so concurrent Java threads do not share).
 struct Scratch {

@@ -147,7 +147,7 @@ class SlabFft3d:
     """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
 
     def __init__(self, dims, group=None, exchange="pipe", engine=None, device=None, groups=None,
-                 exchange_ctas=None, chunks=None, bulk_store=None, graph=None):
+                 exchange_ctas=None, chunks=None, bulk_store=None, graph=None, order=None, head_ctas=None):
         if len(dims) != 3:
             raise ValueError("SlabFft3d needs three dimensions")
         self.group = group
@@ -184,7 +184,7 @@ class SlabFft3d:
                                                 arr(self.peer[0].ptrs), arr(self.peer[1].ptrs), arr(self.flags.ptrs)))
                 self._slab = h
                 for name, value in (("groups", groups), ("exchange_ctas", exchange_ctas), ("chunks", chunks),
-                                    ("bulk_store", bulk_store), ("graph", graph)):
+                                    ("bulk_store", bulk_store), ("graph", graph), ("order", order), ("head_ctas", head_ctas)):
                     if value is not None:
                         _lib.check(lib.sstc_slab_set_option(h, name.encode(), int(value)))
                 torch.cuda.synchronize(dev)
@@ -268,6 +268,19 @@ class SlabFft3d:
                            inverse=True)
         e.axis(slab, slab, self.x_loc * self.d1, self.d2, 1, inverse=True, scale=1.0 / self.n_total)  # z
         return slab
+
+    def set_option(self, name, value):
+        _lib.check(_lib.lib().sstc_slab_set_option(self._slab, name.encode(), int(value)))
+
+    def trace(self):
+        """[(label, ms since the step's start)] of the last step issued with option "trace" = 1."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = _lib.lib().sstc_slab_trace(self._slab, buf, len(buf))
+        return [(a, float(b)) for a, b in (ln.split("\t") for ln in buf.raw[:n].decode().splitlines())]
+
+    def graph_count(self):
+        """Recorded CUDA graphs on the C side (0 while the schedule is still issued eagerly)."""
+        return int(_lib.lib().sstc_slab_graph_count(self._slab)) if self._slab is not None else 0
 
     def launches_per_forward(self):
         return 3

@@ -588,3 +588,52 @@ def test_c4_device_tier_properties():
     want = a.view(m, m) @ b.view(m, m)
     assert (torch.linalg.norm(c.view(m, m) - want) / torch.linalg.norm(want)).item() < 1e-12 * 12
     torch.cuda.synchronize()
+
+
+@needs_ref
+def test_c4_full_size_against_reference(k):
+    """BASELINE.json configs[3]'s own size, 8192 x 8192, against the reference's compiled C++ on the same input (host
+    tier): riOp and the reductions' index / extremum results bit-exact, the scans and sums within 1e-12 * log2 N. The
+    integer-valued input makes every partial sum exact, so the scan must agree BIT FOR BIT whatever the summation order."""
+    n = 8192
+    dims, st = [n, n], [n, 1]
+    rng = np.random.default_rng(8192)
+    x = rng.integers(-1000, 1000, n * n).astype(np.float64)
+    # riOp MAX / MIN along dim 1 (bit-exact: positions of the extrema, then -1 padding; ties are frequent here)
+    for op in ("RI_MAX", "RI_MIN"):
+        want, got = np.zeros(n * n, dtype=np.int32), np.zeros(n * n, dtype=np.int32)
+        ref.riOp(OP[op], x.copy(), dims, st, want, 1)
+        k.riOp(OP[op], x.copy(), dims, st, got, 1)
+        assert np.array_equal(got, want), op
+    # rdOp SUM / PROD-free scans along dim 1, dim 0 and both: exact on integers
+    for opdims in ((1,), (0,), (0, 1)):
+        want, got = np.zeros(n * n), np.zeros(n * n)
+        ref.rdOp(OP["RD_SUM"], x, dims, st, want, *opdims)
+        k.rdOp(OP["RD_SUM"], x, dims, st, got, *opdims)
+        assert np.array_equal(got, want), opdims
+    # rrOp SUM / MAX / MIN over each dimension: exact on integers
+    for dim, dd, ds in ((1, [n, 1], [1, 1]), (0, [1, n], [n, 1])):
+        for op in ("RR_SUM", "RR_MAX", "RR_MIN"):
+            want, got = np.zeros(n), np.zeros(n)
+            ref.rrOp(OP[op], x, dims, st, want, dd, ds, dim)
+            k.rrOp(OP[op], x, dims, st, got, dd, ds, dim)
+            assert np.array_equal(got, want), (op, dim)
+    # on reals: the scan and the variance within the floating-point tolerance
+    y = rng.uniform(-0.5, 0.5, n * n)
+    want, got = np.zeros(n * n), np.zeros(n * n)
+    ref.rdOp(OP["RD_SUM"], y, dims, st, want, 0, 1)
+    k.rdOp(OP["RD_SUM"], y, dims, st, got, 0, 1)
+    assert rel(got, want) < tol(n * n)
+    want, got = np.zeros(n), np.zeros(n)
+    ref.rrOp(OP["RR_VAR"], y, dims, st, want, [n, 1], [1, 1], 1)
+    k.rrOp(OP["RR_VAR"], y, dims, st, got, [n, 1], [1, 1], 1)
+    assert rel(got, want) < tol(n * n)
+    # ruOp / eOp: IEEE-exact maps, bit for bit
+    a, b = y.copy(), y.copy()
+    ref.ruOp(OP["RU_MUL"], 1.0000001, a)
+    k.ruOp(OP["RU_MUL"], 1.0000001, b)
+    assert np.array_equal(a, b)
+    want, got = np.zeros(n * n), np.zeros(n * n)
+    ref.eOp(OP["RE_ADD"], x, y, want, False)
+    k.eOp(OP["RE_ADD"], x, y, got, False)
+    assert np.array_equal(got, want)

@@ -33,7 +33,7 @@ def one_gpu_reference(dims, full):
 
 
 @pytest.mark.parametrize("dims", [[64, 64, 64], [128, 64, 32], [256, 256, 256]], ids=lambda d: "x".join(map(str, d)))
-@pytest.mark.parametrize("bulk", [0, 1], ids=["stores", "bulk"])
+@pytest.mark.parametrize("bulk", [0, 1, 2], ids=["stores", "bulk", "pipelined"])
 def test_single_process_sharded_matches_one_gpu(dims, bulk):
     import torch
     from shared_b200.sharded import ShardedFft3d, gather_transposed

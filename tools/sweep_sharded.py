@@ -19,11 +19,13 @@ dims = [512, 512, 512]
 n_loc = dims[0] * dims[1] * dims[2] // world
 x = torch.rand(n_loc, 2, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) - 0.5
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-configs = [dict(chunks=c, groups=g, exchange_ctas=k) for (c, g, k) in
-           [(1, 4, sms), (2, 4, sms), (4, 4, sms), (4, 8, sms), (8, 4, sms), (4, 4, 2 * sms), (4, 4, sms + sms // 2),
-            (2, 8, sms), (4, 2, sms)]]
+KEYS = ("order", "chunks", "groups", "exchange_ctas", "head_ctas", "bulk_store")
+configs = [dict(zip(KEYS, v)) for v in
+           [(0, 4, 4, sms, 0, 0), (1, 2, 4, sms, 0, 0), (1, 2, 4, sms, 2 * sms, 0), (1, 2, 4, sms, sms, 0), (1, 2, 2, sms, 0, 0),
+            (1, 2, 8, sms, 0, 0), (1, 4, 4, sms, 0, 0), (1, 2, 4, 2 * sms, 0, 0), (1, 2, 4, sms, 0, 2), (1, 2, 4, sms, 2 * sms, 2),
+            (1, 4, 2, sms, 0, 0), (1, 8, 4, sms, 0, 0)]]
 if len(sys.argv) > 1:
-    configs = [dict(zip(("chunks", "groups", "exchange_ctas"), map(int, a.split(",")))) for a in sys.argv[1:]]
+    configs = [dict(zip(KEYS, map(int, a.split(",")))) for a in sys.argv[1:]]
 ref, out = None, []
 for cfg in configs:
     slab = SlabFft3d(dims, exchange="pipe", device=local, **cfg)
@@ -46,7 +48,7 @@ for cfg in configs:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = torch.tensor([int(same and torch.equal(slab.forward(x), ref))], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    out.append(dict(cfg, ms=round(t.item(), 4), chunks_used=slab.chunks, groups_used=slab.groups, bit_identical=bool(ok.item())))
+    out.append(dict(cfg, ms=round(t.item(), 4), bit_identical=bool(ok.item())))
     torch.cuda.synchronize()
     dist.barrier()
     slab.close()
