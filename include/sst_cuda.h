@@ -73,14 +73,24 @@ int sstc_fft_lengths(int kind, int rank, const int32_t *dims, int64_t *in_len, i
 int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t in_len, double *out,
         int64_t out_len);
 
+/* FftService.setHint("devices", "0,1,2,3") on the C side: with two or more devices named, host-tier 3-D c2c transforms
+ * whose shape the slab transform accepts (device count divides d0 and d1, d2 a power of two in [8, 4096], at least 8 MiB
+ * per device) run over all of them through sstc_fft3d_sharded_host; everything else stays on the calling thread's
+ * device. ndev <= 1 returns to one device. Errors: "Invalid device", "Duplicate device". */
+int sstc_fft_set_devices(int ndev, const int32_t *devices);
+
 /* Tunables of the host tier (process-wide; the FftService.setHint analogue for the transfer side). Names:
  *   "slots"        transforms that may be in flight at once per device (default 2; each holds its own device buffers,
  *                  streams and pinned staging ring, so that one caller's D2H overlaps another's H2D);
- *   "copy_threads" threads that move pageable arrays through the pinned staging ring (default min(8, cores/2));
+ *   "copy_threads" threads that move pageable arrays through the pinned staging ring (default min(12, 3/4 of the cores));
  *   "chunk_mib"    staging / pipelining granularity (default 32);
  *   "pipeline"     0 = H2D, all passes, D2H strictly one after the other (for A/B measurements), 1 = default.
  * Environment: SSTC_HOST_SLOTS, SSTC_HOST_COPY_THREADS, SSTC_HOST_CHUNK_MIB, SSTC_HOST_PIPELINE. */
 int sstc_host_option(const char *name, int64_t value);
+/* Where the calling thread's last sstc_fft spent its time (milliseconds): out[0..11] = total, input phase (H2D + inner
+ * axes), output phase (outermost axis + D2H), host copies pageable -> ring, ring -> pageable, host blocked on a ring
+ * buffer's DMA (in, out), pipelined?, in pinned?, out pinned?, input chunks, output groups. */
+int sstc_host_last_stats(double *out, int n);
 
 /* DEVICE tier. A plan replaces the fftw_plan held by org.sharedx.fftw.Plan (Plan.cpp:101-141 create,
  * :143-175 destroy); creation is serialised internally, execution is re-entrant per stream. */

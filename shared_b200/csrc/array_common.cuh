@@ -79,4 +79,10 @@ __device__ __forceinline__ double java_min(double a, double b) {
     return (a != a) ? a : ((b != b) ? b : r);
 }
 
+// Single-pass 2-D inclusive sum scan of a dense row-major (rows x cols) array (array_scan2d.cu). `border`: the input is the
+// destination with its interior replaced by the source shifted by (1, 1), which is ImageKernel.createIntegralImage.
+bool scan2d_applicable(int64_t rows, int64_t cols);
+void scan2d_sum(const double *src, int64_t spitch, double *dst, int64_t dpitch, int64_t rows, int64_t cols, bool border,
+        cudaStream_t stream);
+
 }  // namespace sstc

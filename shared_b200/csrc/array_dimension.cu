@@ -1200,6 +1200,15 @@ int sstc_rdop_dev(int type, const double *src, int64_t nsrc, const int32_t *sD, 
         if (nsrc == 0) {
             return;
         }
+        // both dimensions of a dense 2-D array: one pass over the data instead of one per dimension (array_scan2d.cu)
+        if (type == RD_SUM && nd == 2 && flag[0] && flag[1] && sD[0] > 1 && sD[1] > 1) {
+            const bool row_major = sS[1] == 1 && sS[0] == sD[1], col_major = sS[0] == 1 && sS[1] == sD[0];
+            const int64_t rows = row_major ? sD[0] : sD[1], cols = row_major ? sD[1] : sD[0];
+            if ((row_major || col_major) && scan2d_applicable(rows, cols)) {
+                scan2d_sum(src, cols, dst, cols, rows, cols, false, s);
+                return;
+            }
+        }
         std::vector<int64_t> d = widen(sD, nd), st = widen(sS, nd);
         const double *cur = src;
         bool any = false;

@@ -173,6 +173,17 @@ int sstc_integral_image_dev(const double *src, int64_t nsrc, const int32_t *sD, 
         if (nsrc == 0) {
             return;
         }
+        // 2-D dense images: ONE pass -- every source element read once, every destination element written once; the
+        // copy to offset (1, 1) and both scans happen in the tile (array_scan2d.cu)
+        if (nd == 2 && sD[0] > 0 && sD[1] > 0) {
+            const bool row_major = dS[1] == 1 && dS[0] == dD[1] && sS[1] == 1 && sS[0] == sD[1];
+            const bool col_major = dS[0] == 1 && dS[1] == dD[0] && sS[0] == 1 && sS[1] == sD[0];
+            const int64_t rows = row_major ? dD[0] : dD[1], cols = row_major ? dD[1] : dD[0];
+            if ((row_major || col_major) && scan2d_applicable(rows, cols)) {
+                scan2d_sum(src, cols - 1, dst, cols, rows, cols, true, as_stream(stream));
+                return;
+            }
+        }
         // Fused path: dimension 0 is not the fastest one and there are enough lines for coalesced strips -- the copy
         // is folded into the first scan (8 B read + 8 B written per point instead of 32), the other dimensions are
         // scanned in place afterwards.

@@ -288,6 +288,19 @@ JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaFftService_transform(JNIEnv *en
     raise_last(env, rc);
 }
 
+JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaFftService_setDevices(JNIEnv *env, jobject, jintArray devices) {
+    if (!devices) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize n = len(env, devices);
+    int rc;
+    {
+        Pin d(env, devices, true);
+        rc = sstc_fft_set_devices(n, d.as<int32_t>());
+    }
+    raise_last(env, rc);
+}
+
 // ---- ArrayKernel (Bindings.cpp:26-119) ---------------------------------------------------------------------------
 
 JNIEXPORT void JNICALL AK(randomize)(JNIEnv *env, jobject) { raise_last(env, sstc_srand((uint64_t) time(nullptr))); }

@@ -55,16 +55,27 @@ class CudaFftService:
         """FftService.ifft (FftService.java:86): backward c2c, scaled by 1/N."""
         self._transform(BACKWARD, dims, in_, out)
 
+    # hint name -> (validator / action, getter); FftService.setHint / getHint (FftService.java:96-105)
+    _MODES = ("estimate", "measure", "patient", "exhaustive")
+
     def setHint(self, name, value):
-        """FftService.setHint (FftService.java:96). FFTW's "mode"/"wisdom" hints (FftwService.java:93-122)
-        are accepted and ignored (plans here are deterministic); anything else -> "Unknown hint"
-        (JavaFftService.java:96-99 raises IllegalArgumentException)."""
+        """FftService.setHint (FftService.java:96). FFTW's "mode" / "wisdom" hints (FftwService.java:93-122) are accepted
+        for compatibility (plans here are deterministic); "devices" = comma-separated CUDA device ordinals: with two or
+        more, eligible 3-D c2c transforms run slab-sharded over all of them (sstc_fft_set_devices). Anything else ->
+        "Unknown hint" (JavaFftService.java:96-99 raises IllegalArgumentException)."""
         if name == "mode":
-            if value not in ("estimate", "measure", "patient", "exhaustive"):
+            if value not in self._MODES:
                 raise ValueError("Invalid execution mode")
             self._hints["mode"] = value
         elif name == "wisdom":
             self._hints["wisdom"] = ""
+        elif name == "devices":
+            try:
+                devs = [int(v) for v in value.split(",") if v.strip() != ""]
+            except ValueError:
+                raise ValueError("Invalid device list") from None
+            _lib.check(_lib.lib().sstc_fft_set_devices(len(devs), _lib.i32_array(devs)))
+            self._hints["devices"] = ",".join(str(d) for d in devs)
         else:
             raise ValueError("Unknown hint")
 
@@ -74,6 +85,8 @@ class CudaFftService:
             return self._hints.get("mode", "estimate")
         if name == "wisdom":
             return ""
+        if name == "devices":
+            return self._hints.get("devices", "")
         raise ValueError("Unknown hint")
 
 

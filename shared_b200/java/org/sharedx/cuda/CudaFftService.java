@@ -24,8 +24,12 @@ public class CudaFftService implements FftService {
     final public static int FORWARD = 2;
     final public static int BACKWARD = 3;
 
-    /** FFTW's planner modes are accepted for compatibility and ignored: plans here are deterministic. */
-    volatile String mode = "estimate";
+    /** Hints this provider knows, with their current values (FFTW's planner hints are accepted for compatibility). */
+    final private java.util.Map<String, String> hints = new java.util.concurrent.ConcurrentHashMap<String, String>();
+
+    /** Values "mode" may take (FFTW's planner rigor levels; plans here are deterministic, so they change nothing). */
+    final private static java.util.Set<String> MODES = new java.util.HashSet<String>(
+            java.util.Arrays.asList("estimate", "measure", "patient", "exhaustive"));
 
     /**
      * Public and without arguments: {@code Services.createService} instantiates providers reflectively. Refuses to exist
@@ -62,45 +66,55 @@ public class CudaFftService implements FftService {
         transform(BACKWARD, dims, in, out);
     }
 
+    /** JNI: Java_org_sharedx_cuda_CudaFftService_setDevices -> sstc_fft_set_devices. */
+    final native void setDevices(int[] devices);
+
+    /**
+     * Hints: {@code "mode"} and {@code "wisdom"} as {@code FftwService} takes them; {@code "devices"}, a comma-separated
+     * list of CUDA device ordinals -- with two or more, 3-D complex transforms whose shape allows it run slab-sharded
+     * over all of them, every device moving its part of the array over its own PCIe link.
+     */
     @Override
     public void setHint(String name, String value) {
 
-        if (name.equals("mode")) {
+        if ("mode".equals(name)) {
 
-            if (value.equals("estimate") || value.equals("measure") //
-                    || value.equals("patient") || value.equals("exhaustive")) {
-
-                this.mode = value;
-
-            } else {
-
+            if (!MODES.contains(value)) {
                 throw new IllegalArgumentException("Invalid execution mode");
             }
 
-        } else if (name.equals("wisdom")) {
+        } else if ("devices".equals(name)) {
 
-            // Nothing to import: there is no planner state.
+            String[] parts = value.trim().isEmpty() ? new String[0] : value.split(",");
+            int[] devices = new int[parts.length];
 
-        } else {
+            for (int i = 0; i < parts.length; i++) {
+
+                try {
+                    devices[i] = Integer.parseInt(parts[i].trim());
+                } catch (NumberFormatException e) {
+                    throw new IllegalArgumentException("Invalid device list");
+                }
+            }
+
+            setDevices(devices);
+
+        } else if (!"wisdom".equals(name)) {
 
             throw new IllegalArgumentException("Unknown hint");
         }
+
+        this.hints.put(name, "wisdom".equals(name) ? "" : value);
     }
 
     @Override
     public String getHint(String name) {
 
-        if (name.equals("mode")) {
-
-            return this.mode;
-
-        } else if (name.equals("wisdom")) {
-
-            return "";
-
-        } else {
-
+        if (!"mode".equals(name) && !"wisdom".equals(name) && !"devices".equals(name)) {
             throw new IllegalArgumentException("Unknown hint");
         }
+
+        String value = this.hints.get(name);
+        return value != null ? value : ("mode".equals(name) ? "estimate" : "");
     }
 }

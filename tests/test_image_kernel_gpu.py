@@ -35,7 +35,9 @@ CASES = [([1], "FAR"), ([7], "FAR"), ([300], "FAR"), ([5, 9], "FAR"), ([5, 9], "
          ([257, 300], "NEAR"), ([3, 4, 5], "FAR"), ([3, 4, 5], "NEAR"), ([20, 31, 17], "FAR"), ([2, 3, 2, 4], "NEAR"),
          ([1, 6], "FAR"), ([6, 1], "NEAR"),
          # enough lines off dimension 0 for the fused copy + first scan
-         ([70, 1500], "FAR"), ([40, 30, 50], "FAR"), ([300, 40, 33], "FAR"), ([3, 2000], "FAR"), ([1500, 70], "NEAR")]
+         ([70, 1500], "FAR"), ([40, 30, 50], "FAR"), ([300, 40, 33], "FAR"), ([3, 2000], "FAR"), ([1500, 70], "NEAR"),
+         # 2-D images large enough for the single-pass tile scan (array_scan2d.cu): ragged tiles, both orders, one thin
+         ([1000, 1030], "FAR"), ([513, 2049], "NEAR"), ([63, 1100], "FAR"), ([4097, 65], "FAR")]
 
 
 @needs_ref

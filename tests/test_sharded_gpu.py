@@ -91,3 +91,44 @@ def test_one_process_per_gpu_matches_one_gpu():
                           "--small"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "FAIL" not in res.stdout
+
+
+def test_devices_hint_routes_the_provider_call_over_all_gpus():
+    """FftService.setHint("devices", ...): the same provider call (sstc_fft on host arrays), served by the slab transform
+    over every named device; checked against the CPU oracle, then back on one device with the same bits as before."""
+    import oracle
+    import shared_b200 as s
+    p = min(devices(), 8)
+    if p < 2:
+        pytest.skip("needs at least two GPUs")
+    p = 1 << int(math.log2(p))
+    svc = s.CudaFftService(0)
+    dims = [128, 128, 128]
+    n = 128 ** 3
+    x = np.random.default_rng(77).uniform(-0.5, 0.5, 2 * n)
+    one = np.empty_like(x)
+    svc.fft(dims, x, one)
+    try:
+        svc.setHint("devices", ",".join(str(d) for d in range(p)))
+        assert svc.getHint("devices") == ",".join(str(d) for d in range(p))
+        many = np.empty_like(x)
+        svc.fft(dims, x, many)
+        want = oracle.fft(dims, x)
+        assert np.linalg.norm(many - want) / np.linalg.norm(want) < 1e-12 * math.log2(n)
+        assert np.linalg.norm(many - one) / np.linalg.norm(one) < 1e-13
+        back = np.empty_like(x)
+        svc.ifft(dims, many, back)
+        assert np.linalg.norm(back - x) / np.linalg.norm(x) < 1e-12 * math.log2(n)
+        # shapes the slab transform does not take stay on one device
+        small = np.random.default_rng(78).uniform(-0.5, 0.5, 2 * 6 * 10 * 12)
+        out = np.empty_like(small)
+        svc.fft([6, 10, 12], small, out)
+        want = oracle.fft([6, 10, 12], small)
+        assert np.linalg.norm(out - want) / np.linalg.norm(want) < 1e-13
+        with pytest.raises(s.SstCudaError, match="Invalid device"):
+            svc.setHint("devices", "0,99")
+    finally:
+        svc.setHint("devices", "")
+    again = np.empty_like(x)
+    svc.fft(dims, x, again)
+    assert np.array_equal(again, one)
