@@ -231,8 +231,10 @@ int sstc_peer_barrier_dev(void *const *d_flag_arrays, int nranks, int rank, uint
  * shared memory in pieces of `piece` bytes (cp.async.bulk in, cp.async.bulk out). Not used by any transform. */
 int sstc_exp_peer_copy(void *dst, const void *src, int64_t bytes, int mode, int piece, int ctas, void *stream);
 
-/* Diagnostics knob for tools/exp_overlap.py: "exchange_smem_kb" = dynamic shared memory the pipelined exchange kernel
- * requests (beyond its need), which keeps other kernels' CTAs off its SMs. */
+/* Diagnostics knobs: "exchange_smem_kb" = dynamic shared memory the pipelined exchange kernel requests (beyond its need),
+ * which keeps other kernels' CTAs off its SMs (tools/exp_overlap.py); "tma_strided" = 1 / 2 / 3: the 512- and 4096-point
+ * strided passes move their tiles with TMA (cp.async.bulk.tensor) with that many tile buffers per CTA instead of per-thread
+ * loads and stores (tools/exp_tma.py; 0 = off, the default). */
 int sstc_exp_set(const char *name, int64_t value);
 
 /* Cross-process device-memory sharing for the one-process-per-GPU layout (cudaIpc*): export a 64-byte

@@ -21,6 +21,7 @@
 // per point.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -599,6 +600,120 @@ __global__ void __launch_bounds__(ExchangeTile<L, C>::THREADS, 2) fft_exchange_k
     }
     if (tid == 0) {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every line has been written before the CTA retires
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// A strided pass with TMA tile movement (experiment): the (L x C) tile -- C adjacent columns, row stride
+// `inner` -- is described by a 3-D tensor map (2C doubles x L rows x planes) and moved by cp.async.bulk.tensor (SASS
+// UTMALDG / UTMASTG) in boxes of 256 rows: one elected thread issues the copies, completion arrives on an mbarrier, and
+// the tile lands in shared memory in exactly the layout the Stockham stages exchange through (row-major, C columns).
+// NBUF = 1: one tile per CTA turn, load -> stages -> store, as many CTAs per SM as shared memory allows (the register
+// path's structure with the LSU taken out of the tile movement). NBUF = 3: persistent CTAs, the next tile is pulled in
+// while the current one is transformed and the previous one drains (the exchange kernel's structure).
+// ---------------------------------------------------------------------------------------------------------
+template <int L, int C, int NBUF>
+struct TmaTile {
+    static constexpr int T = L / 8;
+    static constexpr int THREADS = C * T;
+    static constexpr int BUF_ELEMS = Pow2Tile<L, C, true>::LINE * C;  // the stages' layout pads narrow tiles (C < 8)
+    static constexpr int BOX_ROWS = L < 256 ? L : 256;
+    static constexpr int SMEM_BYTES = NBUF * BUF_ELEMS * 16 + 128;
+    // as many CTAs per SM as shared memory allows, with the registers to match
+    static constexpr int MIN_CTAS = (227 * 1024) / SMEM_BYTES < 1 ? 1 : ((227 * 1024) / SMEM_BYTES) * THREADS > 1024
+                    ? (1024 / THREADS < 1 ? 1 : 1024 / THREADS) : (227 * 1024) / SMEM_BYTES;
+};
+
+__device__ __forceinline__ void tma_load_3d(void *smem, const void *map, int x, int y, int z, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                         (uint32_t) __cvta_generic_to_shared(smem)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const void *map, int x, int y, int z, const void *smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y), "r"(z),
+                 "r"((uint32_t) __cvta_generic_to_shared(smem))
+                 : "memory");
+}
+
+template <int L, int C, int NBUF>
+__global__ void __launch_bounds__(TmaTile<L, C, NBUF>::THREADS, TmaTile<L, C, NBUF>::MIN_CTAS) fft_pow2_tma_kernel(const __grid_constant__ CUtensorMap in_map,
+        const __grid_constant__ CUtensorMap out_map, const FftPassArgs a) {
+    using Tile = TmaTile<L, C, NBUF>;
+    constexpr int T = Tile::T;
+    extern __shared__ __align__(128) double2 sm[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + NBUF * Tile::BUF_ELEMS);
+    const int tid = threadIdx.x, c = tid % C, t = tid / C;
+    const int64_t tiles_per_plane = (a.inner + C - 1) / C;
+    const int64_t ntiles = a.ntiles;
+
+    auto issue_load = [&](int64_t tile, int b) {
+        const uint32_t bar = (uint32_t) __cvta_generic_to_shared(&bars[b]);
+        const int o = (int) (tile / tiles_per_plane);
+        const int x = (int) ((tile - (int64_t) o * tiles_per_plane) * C * 2);  // in doubles
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t) (L * C * 16)) : "memory");
+#pragma unroll
+        for (int y = 0; y < L; y += Tile::BOX_ROWS) {
+            tma_load_3d(sm + b * Tile::BUF_ELEMS + y * C, &in_map, x, y, o, bar);
+        }
+    };
+
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t) __cvta_generic_to_shared(&bars[b])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (NBUF > 1 && (int64_t) blockIdx.x < ntiles) {
+            issue_load(blockIdx.x, 0);
+        }
+    }
+    __syncthreads();
+
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int b = (int) (it % NBUF);
+        double2 *buf = sm + b * Tile::BUF_ELEMS;
+        if (tid == 0) {
+            if (NBUF > 1) {
+                if (tile + gridDim.x < ntiles) {
+                    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF > 2 ? 1 : 0) : "memory");
+                    issue_load(tile + gridDim.x, (int) ((it + 1) % NBUF));
+                }
+            } else {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's store has left the buffer
+                issue_load(tile, 0);
+            }
+        }
+        mbar_wait((uint32_t) __cvta_generic_to_shared(&bars[b]), (uint32_t) ((it / NBUF) & 1));
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const double2 z = buf[(t + m * T) * C + c];
+            v[m] = a.inverse ? make_double2(z.y, z.x) : z;
+        }
+        __syncthreads();  // the tile has been read: the buffer becomes the stages' exchange area (same layout)
+        Pow2Stages<L, C, true, 1>::run(v, t, c, buf, a.tw);
+        __syncthreads();
+        const double s = a.scale;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            buf[(t + m * T) * C + c] = a.inverse ? make_double2(v[m].y * s, v[m].x * s) : make_double2(v[m].x * s, v[m].y * s);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const int o = (int) (tile / tiles_per_plane);
+            const int x = (int) ((tile - (int64_t) o * tiles_per_plane) * C * 2);
+#pragma unroll
+            for (int y = 0; y < L; y += Tile::BOX_ROWS) {
+                tma_store_3d(&out_map, x, y, o, buf + y * C);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 

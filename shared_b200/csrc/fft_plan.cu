@@ -159,6 +159,65 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
     check_launch("fft_pow2_ext_kernel");
 }
 
+// Diagnostics (sstc_exp_set "tma_strided"): 0 = off; 1 = the 512-point strided passes move their tiles with TMA, one
+// tile per CTA turn, two CTAs per SM; 3 = persistent CTAs with three tile buffers (load / transform / store overlapped).
+static std::atomic<int64_t> g_tma_strided{0};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+        CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SSTC_CUDA(cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) {
+            throw std::runtime_error("cuTensorMapEncodeTiled is not available");
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// (outer, L, inner) complex128 viewed as a 3-D tensor of doubles: 2*inner x L x outer, boxes of 2C x box_rows x 1
+static CUtensorMap strided_tile_map(const void *base, int64_t outer, int L, int64_t inner, int C, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t) inner * 2, (cuuint64_t) L, (cuuint64_t) outer};
+    const cuuint64_t strides[2] = {(cuuint64_t) inner * 16, (cuuint64_t) L * (cuuint64_t) inner * 16};
+    const cuuint32_t box[3] = {(cuuint32_t) (2 * C), (cuuint32_t) box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int) r) + ")");
+    }
+    return m;
+}
+
+template <int L, int C, int NBUF>
+static void launch_tma(const FftPassArgs &a0, cudaStream_t stream) {
+    using Tile = TmaTile<L, C, NBUF>;
+    static std::once_flag once[16];
+    static int sms[16];
+    int dev = 0;
+    SSTC_CUDA(cudaGetDevice(&dev));
+    std::call_once(once[dev & 15], [dev] {
+        SSTC_CUDA(cudaFuncSetAttribute(fft_pow2_tma_kernel<L, C, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tile::SMEM_BYTES));
+        SSTC_CUDA(cudaDeviceGetAttribute(&sms[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+    });
+    FftPassArgs a = a0;
+    const int64_t tiles_per_plane = (a.inner + C - 1) / C;
+    a.ntiles = a.outer * tiles_per_plane;
+    const CUtensorMap in_map = strided_tile_map(a.in, a.outer, L, a.inner, C, Tile::BOX_ROWS);
+    const CUtensorMap out_map = strided_tile_map(a.out, a.outer, L, a.inner, C, Tile::BOX_ROWS);
+    const int per_sm = Tile::MIN_CTAS;
+    const int64_t grid = std::min<int64_t>(a.ntiles, (int64_t) sms[dev & 15] * per_sm);
+    fft_pow2_tma_kernel<L, C, NBUF><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(in_map, out_map, a);
+    check_launch("fft_pow2_tma_kernel");
+}
+
 template <int L>
 static void launch_pow2_L(const FftPassArgs &a, bool strided, cudaStream_t stream) {
     if (L == 512) {
@@ -183,6 +242,23 @@ static void launch_pow2_L(const FftPassArgs &a, bool strided, cudaStream_t strea
             }
             return;
         }
+    }
+    const int64_t tma = g_tma_strided.load();
+    if (strided && tma > 0 && (L == 512 || L == 4096) && a.mode == MODE_C2C && a.ksplit == 0 && a.in_ksplit == 0 && !a.mul &&
+            a.crop_cols == 0 && a.in_kstride == a.inner && a.out_kstride == a.inner && a.in_plane == (int64_t) L * a.inner &&
+            a.out_plane == (int64_t) L * a.inner && a.inner * 2 < (1LL << 31) && a.outer < (1LL << 31)) {
+        if (L == 512) {
+            if (tma >= 3) {
+                launch_tma<512, strided_cols(512), 3>(a, stream);
+            } else if (tma == 2) {
+                launch_tma<512, strided_cols(512), 2>(a, stream);
+            } else {
+                launch_tma<512, strided_cols(512), 1>(a, stream);
+            }
+        } else {
+            launch_tma<4096, strided_cols(4096), 1>(a, stream);
+        }
+        return;
     }
     if (strided) {
         constexpr int C = strided_cols(L);
@@ -1065,6 +1141,8 @@ int sstc_exp_set(const char *name, int64_t value) {
     return guarded([&] {
         if (name && std::string(name) == "exchange_smem_kb") {
             g_exchange_smem_kb.store(value);
+        } else if (name && std::string(name) == "tma_strided") {
+            g_tma_strided.store(value);
         } else {
             throw std::runtime_error("Unknown option");
         }

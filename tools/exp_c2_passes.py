@@ -40,6 +40,22 @@ res["c2c_columns_4096_inner2048"] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.
 res["c2c_rows_4096_contig_x2049"] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.data_ptr(), h, n, 1, False, 1.0, st))
 res["c2c_columns_2048_inner4096"] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.data_ptr(), 1, 2048, 4096, False, 1.0, st))
 res["c2c_columns_1024_inner8192"] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.data_ptr(), 1, 1024, 8192, False, 1.0, st))
+# candidates for the long strided axis: a padded, 128-byte-aligned row pitch on the load side, and the column
+# axis as 4 x 1024 (the radix-4 step folded into the r2c pass leaves four 1024-point column transforms, stored interleaved)
+pad = 2056
+wsp = torch.empty(n * pad, 2, dtype=torch.float64, device="cuda")
+res["c2c_columns_4096_padded_pitch_2056_to_dense"] = ev(lambda: s.fft_axis_strided(
+    wsp.data_ptr(), spec.data_ptr(), 1, n, h, n * pad, pad, n * h, h, False, 1.0, st))
+res["c2c_columns_4096_padded_pitch_2056_inplace"] = ev(lambda: s.fft_axis_strided(
+    wsp.data_ptr(), wsp.data_ptr(), 1, n, h, n * pad, pad, n * pad, pad, False, 1.0, st))
+res["c2c_columns_4x1024_padded_in_interleaved_dense_out"] = ev(lambda: s.fft_axis_strided(
+    wsp.data_ptr(), spec.data_ptr(), 4, 1024, h, 1024 * pad, pad, h, 4 * h, False, 1.0, st))
+res["c2c_columns_4x1024_dense_in_interleaved_dense_out"] = ev(lambda: s.fft_axis_strided(
+    spec2.data_ptr(), spec.data_ptr(), 4, 1024, h, 1024 * h, h, h, 4 * h, False, 1.0, st))
+res["c2c_columns_8x512_padded_in_interleaved_dense_out"] = ev(lambda: s.fft_axis_strided(
+    wsp.data_ptr(), spec.data_ptr(), 8, 512, h, 512 * pad, pad, h, 8 * h, False, 1.0, st))
+res["c2c_columns_2x2048_padded_in_interleaved_dense_out"] = ev(lambda: s.fft_axis_strided(
+    wsp.data_ptr(), spec.data_ptr(), 2, 2048, h, 2048 * pad, pad, h, 2 * h, False, 1.0, st))
 p2 = s.FftPlan(s.C2R, [n, n])
 res["rifft_total"] = ev(lambda: p2.execute(spec.data_ptr(), back.data_ptr(), st))
 res["bytes_c2c_pass_MB"] = 2 * 16 * n * h / 1e6
