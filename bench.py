@@ -389,7 +389,7 @@ def run_ours(args):
         worst = max(passes, key=lambda p: p["ms"])
         traffic = None  # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
         try:
-            with open(os.path.join(ROOT, "profiles", "r1_fft512_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r2_fft512_traffic.json")) as f:
                 per = json.load(f)["dram_bytes_read_plus_write_per_launch"]
                 traffic = (per["y"] + per["x"]) / 2
         except Exception:

@@ -234,6 +234,16 @@ def config_c2(torch, s, peak, sampler, with_cpu):
     return res
 
 
+def _i32(v):
+    from shared_b200 import _lib
+    return _lib.i32_array(v)
+
+
+def _structural(name, *args):
+    from shared_b200 import _lib
+    _lib.check(getattr(_lib.lib(), name)(*args))
+
+
 OP = dict(RU_MUL=1, RU_EXP=4, RU_SQRT=7, RE_ADD=0, RE_MUL=2, RR_SUM=0, RR_MAX=2, RR_VAR=4, RD_SUM=0, RI_MAX=0, RA_SUM=0)
 
 
@@ -273,6 +283,12 @@ def config_c4(torch, s, peak, sampler, with_cpu):
             ("riOp MAX dim1", 12, lambda: dk.riOp(OP["RI_MAX"], P, N, [n, n], far, idx.data_ptr(), N, 1)),
             ("map transpose", 16, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], [1, n])),
             ("map copy", 16, lambda: dk.map(8, [0, 0, n, 0, 0, n], P, N, [n, n], far, z.data_ptr(), N, [n, n], far)),
+            ("shift by (n/2, n/2) (sstc_shift_dev: ProtoArray.shift / fftShift)", 16, lambda: _structural(
+                "sstc_shift_dev", 8, ctypes.c_void_p(P), ctypes.c_void_p(z.data_ptr()), _i32([n, n]), 2, 0, _i32([n // 2, n // 2]),
+                ctypes.c_void_p(st))),
+            ("transpose (sstc_transpose_dev)", 16, lambda: _structural(
+                "sstc_transpose_dev", 8, ctypes.c_void_p(P), ctypes.c_void_p(z.data_ptr()), _i32([n, n]), 2, 0, _i32([1, 0]),
+                ctypes.c_void_p(st))),
             ("ImageKernel createIntegralImage", 16, lambda: ik.createIntegralImage(
                 P, N, [n, n], far, ii.data_ptr(), ii.numel(), [n + 1, n + 1], [n + 1, 1])),
         ]

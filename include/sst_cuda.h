@@ -320,6 +320,20 @@ int sstc_slice_dev(int elem_bytes, const int32_t *slices, int nslices3, const vo
         const int32_t *sD, const int32_t *sS, void *dst, int64_t ndst, const int32_t *dD, const int32_t *dS, int nd,
         void *stream);
 
+/* The structural callers of map / slice as single device-tier calls on dense arrays (near_order = 0: row-major FAR,
+ * 1: column-major NEAR; Array.java:240-287). In the reference they live on the JVM side and build an int[] specification
+ * per call: ProtoArray.shift (ProtoArray.java:313-337: element i of dimension d moves to (i + shifts[d]) mod dims[d]),
+ * AbstractComplexArray.fftShift / ifftShift (AbstractComplexArray.java:67-97: dims includes the trailing 2; every other
+ * dimension is shifted by +-dims[d]/2), ProtoArray.transpose (ProtoArray.java:246-283: source dimension d becomes
+ * destination dimension permutation[d]; "Invalid permutation"), ConvolutionCache.pad (ConvolutionCache.java:149-239:
+ * mirror padding by margins[d] on both sides of dimension d, row-major; dst has dims[d] + 2 margins[d]). src != dst. */
+int sstc_shift_dev(int elem_bytes, const void *src, void *dst, const int32_t *dims, int nd, int near_order, const int32_t *shifts,
+        void *stream);
+int sstc_fftshift_dev(const double *src, double *dst, const int32_t *dims, int nd, int inverse, void *stream);
+int sstc_transpose_dev(int elem_bytes, const void *src, void *dst, const int32_t *dims, int nd, int near_order,
+        const int32_t *permutation, void *stream);
+int sstc_pad_dev(const double *src, double *dst, const int32_t *dims, int nd, const int32_t *margins, void *stream);
+
 /* mul / diag (Bindings.cpp:111-119): row-major, inner dimension inferred from the lengths. */
 int sstc_mul(const double *lhs, int64_t nl, const double *rhs, int64_t nr, int lr, int rc, double *dst, int64_t ndst,
         int complex);

@@ -107,6 +107,10 @@ _ARRAY_OPS = {
 for _name, _args in _ARRAY_OPS.items():
     SIGNATURES[_name] = (ctypes.c_int, _args)
     SIGNATURES[_name + "_dev"] = (ctypes.c_int, _args + [ctypes.c_void_p])  # device twin: same arguments + stream
+SIGNATURES["sstc_shift_dev"] = (ctypes.c_int, [_i, _vp, _vp, c_i32_p, _i, _i, c_i32_p, _vp])
+SIGNATURES["sstc_fftshift_dev"] = (ctypes.c_int, [_vp, _vp, c_i32_p, _i, _i, _vp])
+SIGNATURES["sstc_transpose_dev"] = (ctypes.c_int, [_i, _vp, _vp, c_i32_p, _i, _i, c_i32_p, _vp])
+SIGNATURES["sstc_pad_dev"] = (ctypes.c_int, [_vp, _vp, c_i32_p, _i, c_i32_p, _vp])
 SIGNATURES["sstc_srand"] = (ctypes.c_int, [ctypes.c_uint64])
 SIGNATURES["sstc_invert"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _i])
 SIGNATURES["sstc_invert_dev"] = (ctypes.c_int, [_vp, _i64, _vp, _i64, _i, _vp])

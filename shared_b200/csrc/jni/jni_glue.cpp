@@ -18,6 +18,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../../include/sst_cuda.h"
@@ -300,6 +302,116 @@ JNIEXPORT void JNICALL Java_org_sharedx_cuda_CudaFftService_setDevices(JNIEnv *e
     }
     raise_last(env, rc);
 }
+
+// ---- CudaComplexArray: the device-resident twin; static natives, device tier of the C ABI ----------
+// (the class parameter is declared jobject: jclass is a jobject, and the repository's consistency tests read one shape)
+
+#define CA(name) Java_org_sharedx_cuda_CudaComplexArray_##name
+
+JNIEXPORT jlong JNICALL CA(allocate)(JNIEnv *env, jobject, jint nDoubles) {
+    void *p = nullptr;
+    int rc = nDoubles < 0 ? 1 : sstc_malloc(&p, (int64_t) nDoubles * 8);
+    if (rc == 0 && p) {
+        rc = sstc_memset(p, 0, (int64_t) nDoubles * 8, nullptr);
+    }
+    if (nDoubles < 0) {
+        raise(env, "Invalid arguments");
+        return 0;
+    }
+    raise_last(env, rc);
+    return (jlong) (intptr_t) p;
+}
+
+JNIEXPORT void JNICALL CA(free)(JNIEnv *env, jobject, jlong pointer) {
+    raise_last(env, sstc_free((void *) (intptr_t) pointer));
+}
+
+JNIEXPORT void JNICALL CA(upload)(JNIEnv *env, jobject, jlong pointer, jdoubleArray values) {
+    if (!values || !pointer) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize n = len(env, values);
+    int rc;
+    {
+        Pin v(env, values, true);
+        rc = sstc_h2d((void *) (intptr_t) pointer, v.as<double>(), (int64_t) n * 8, nullptr);
+        if (rc == 0) {
+            rc = sstc_stream_sync(nullptr);  // the pinned JVM array must not move before the copy has read it
+        }
+    }
+    raise_last(env, rc);
+}
+
+JNIEXPORT void JNICALL CA(download)(JNIEnv *env, jobject, jlong pointer, jdoubleArray values) {
+    if (!values || !pointer) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize n = len(env, values);
+    int rc;
+    {
+        Pin v(env, values, false);
+        rc = sstc_d2h(v.as<double>(), (const void *) (intptr_t) pointer, (int64_t) n * 8, nullptr);
+        if (rc == 0) {
+            rc = sstc_stream_sync(nullptr);
+        }
+    }
+    raise_last(env, rc);
+}
+
+JNIEXPORT void JNICALL CA(eMul)(JNIEnv *env, jobject, jlong lhs, jlong rhs, jlong dst, jint nDoubles) {
+    // CE_MUL = 2 (ArrayKernel.java:247), complex pairs
+    raise_last(env, sstc_eop_dev(2, SSTC_ELEM_COMPLEX, (const void *) (intptr_t) lhs, (const void *) (intptr_t) rhs,
+                            (void *) (intptr_t) dst, nDoubles, nullptr));
+}
+
+JNIEXPORT void JNICALL CA(transform)(JNIEnv *env, jobject, jint kind, jintArray dims, jlong in, jlong out) {
+    if (!dims || !in || !out) {
+        return raise(env, "Invalid arguments");
+    }
+    // plans are cached per (kind, dims), like FftwService's plan cache (FftwService.java:58-67,221-236)
+    static std::mutex mutex;
+    static std::map<std::vector<int32_t>, sstc_fft_plan> plans;
+    const jsize nd = len(env, dims);
+    std::vector<int32_t> key(1, kind);
+    {
+        Pin d(env, dims, true);
+        key.insert(key.end(), d.as<int32_t>(), d.as<int32_t>() + nd);
+    }
+    int rc = 0;
+    sstc_fft_plan plan = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mutex);
+        auto it = plans.find(key);
+        if (it == plans.end()) {
+            rc = sstc_fft_plan_create(&plan, kind, nd, key.data() + 1);
+            if (rc == 0) {
+                plans[key] = plan;
+            }
+        } else {
+            plan = it->second;
+        }
+    }
+    if (rc == 0) {
+        rc = sstc_fft_plan_execute(plan, (const double *) (intptr_t) in, (double *) (intptr_t) out, nullptr);
+    }
+    raise_last(env, rc);
+}
+
+JNIEXPORT void JNICALL CA(fftShift)(JNIEnv *env, jobject, jlong src, jlong dst, jintArray dims, jboolean inverse) {
+    if (!dims || !src || !dst) {
+        return raise(env, "Invalid arguments");
+    }
+    const jsize nd = len(env, dims);
+    std::vector<int32_t> d;
+    {
+        Pin p(env, dims, true);
+        d.assign(p.as<int32_t>(), p.as<int32_t>() + nd);
+    }
+    raise_last(env, sstc_fftshift_dev((const double *) (intptr_t) src, (double *) (intptr_t) dst, d.data(), nd, inverse ? 1 : 0,
+                            nullptr));
+}
+
+JNIEXPORT void JNICALL CA(synchronize)(JNIEnv *env, jobject) { raise_last(env, sstc_stream_sync(nullptr)); }
 
 // ---- ArrayKernel (Bindings.cpp:26-119) ---------------------------------------------------------------------------
 

@@ -60,7 +60,7 @@ def test_jni_glue_covers_every_java_native():
     method (the glue cannot be linked here -- no JDK -- so this is what keeps the two sides from drifting apart)."""
     java_dir = os.path.join(ROOT, "shared_b200", "java", "org", "sharedx", "cuda")
     glue = open(os.path.join(ROOT, "shared_b200", "csrc", "jni", "jni_glue.cpp")).read()
-    glue = glue.replace("AK(", "Java_org_sharedx_cuda_CudaArrayKernel_(")
+    glue = glue.replace("AK(", "Java_org_sharedx_cuda_CudaArrayKernel_(").replace("CA(", "Java_org_sharedx_cuda_CudaComplexArray_(")
     exported = set(re.findall(r"Java_org_sharedx_cuda_(\w+?)_\(?(\w+)\)?\s*\(JNIEnv", glue))
     declared = set()
     for f in os.listdir(java_dir):
@@ -116,6 +116,7 @@ def test_jni_export_signatures_match_the_java_natives():
     java_dir = os.path.join(ROOT, "shared_b200", "java", "org", "sharedx", "cuda")
     glue = open(os.path.join(ROOT, "shared_b200", "csrc", "jni", "jni_glue.cpp")).read()
     glue = re.sub(r"\bAK\((\w+)\)", r"Java_org_sharedx_cuda_CudaArrayKernel_\1", glue)
+    glue = re.sub(r"\bCA\((\w+)\)", r"Java_org_sharedx_cuda_CudaComplexArray_\1", glue)
     jtype = {"double[]": "jdoubleArray", "int[]": "jintArray", "int": "jint", "double": "jdouble", "boolean": "jboolean",
              "long": "jlong", "void": "void", "V": "jobject", "int...": "jintArray", "Object": "jobject", "SparseArrayState<V>": "jobject"}
     exports = {}
