@@ -42,6 +42,7 @@ struct sstc_slab_s {
     size_t next_event = 0;
     int groups = 4, chunks = 1, exchange_ctas = 0, bulk = 0, use_graph = 1;
     int order = 0, head_ctas = 0;  // see issue_forward
+    int split_barrier = 0;         // see barrier_after_exchange
     uint64_t step = 0;
     std::map<std::tuple<int, const void *, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, const void *, int>, int64_t> graph_kernels;
@@ -95,12 +96,21 @@ static int pick_divisor(int want, int of) {
 }
 
 // Cross-rank barrier behind the exchange kernel just issued on s_z; the event it returns fires when every rank has
-// passed it. The signal is issued on s_z itself, so that it leaves ahead of the next exchange kernel's data; the wait
-// runs on the high-priority side stream.
+// passed it. Default: one kernel on the high-priority side stream publishes this rank's flag and waits for the peers'.
+// split_barrier = 1: the SIGNAL is issued on s_z itself, so that it leaves ahead of the next exchange kernel's data (a flag
+// written while the next group's lines are already streaming queues behind them and arrives 50-80 us late: the step trace,
+// profiles/r2_sharded_8gpu_sweeps_and_traces.json), and only the WAIT runs on the side stream. The x passes then start
+// earlier, but the step does not get shorter (0.525 against 0.514 ms at 8 GPUs: the extra kernel between the exchange
+// launches costs what the earlier start gains, because the passes that run beside the exchange slow it down either way).
 static cudaEvent_t barrier_after_exchange(sstc_slab_s &S) {
-    launch_peer_signal(S.flags, S.nranks, S.rank, S.s_z);
-    SSTC_CUDA(cudaStreamWaitEvent(S.s_bar, record_on(S, S.s_z), 0));
-    launch_peer_wait(S.flags, S.nranks, S.rank, S.s_bar);
+    if (S.split_barrier) {
+        launch_peer_signal(S.flags, S.nranks, S.rank, S.s_z);
+        SSTC_CUDA(cudaStreamWaitEvent(S.s_bar, record_on(S, S.s_z), 0));
+        launch_peer_wait(S.flags, S.nranks, S.rank, S.s_bar);
+    } else {
+        SSTC_CUDA(cudaStreamWaitEvent(S.s_bar, record_on(S, S.s_z), 0));
+        launch_peer_barrier(S.flags, S.nranks, S.rank, 0, S.s_bar);
+    }
     return record_on(S, S.s_bar);
 }
 
@@ -509,6 +519,10 @@ int sstc_slab_set_option(sstc_slab slab, const char *name, int64_t value) {
             slab->bulk = (int) value;
         } else if (n == "order") {
             slab->order = value ? 1 : 0;
+        } else if (n == "split_barrier") {
+            // both styles count their calls in the rank's own flag slots: switch only while no step is in flight, and on
+            // every rank alike
+            slab->split_barrier = value ? 1 : 0;
         } else if (n == "head_ctas") {
             slab->head_ctas = (int) value;
         } else if (n == "graph") {

@@ -117,6 +117,7 @@ __global__ void peer_barrier_kernel(PeerFlags f, int nranks, int rank, unsigned 
         __shared__ unsigned long long next;
         if (r == 0) {
             next = ++f.ptr[rank][8];
+            f.ptr[rank][9] = next;  // the split barrier's wait counter stays in step (a context may switch styles)
         }
         __syncthreads();
         epoch = next;

@@ -147,7 +147,8 @@ class SlabFft3d:
     """3-D c2c transform of (d0, d1, d2), slab-sharded over the ranks of `group`."""
 
     def __init__(self, dims, group=None, exchange="pipe", engine=None, device=None, groups=None,
-                 exchange_ctas=None, chunks=None, bulk_store=None, graph=None, order=None, head_ctas=None):
+                 exchange_ctas=None, chunks=None, bulk_store=None, graph=None, order=None, head_ctas=None,
+                 split_barrier=None):
         if len(dims) != 3:
             raise ValueError("SlabFft3d needs three dimensions")
         self.group = group
@@ -184,7 +185,8 @@ class SlabFft3d:
                                                 arr(self.peer[0].ptrs), arr(self.peer[1].ptrs), arr(self.flags.ptrs)))
                 self._slab = h
                 for name, value in (("groups", groups), ("exchange_ctas", exchange_ctas), ("chunks", chunks),
-                                    ("bulk_store", bulk_store), ("graph", graph), ("order", order), ("head_ctas", head_ctas)):
+                                    ("bulk_store", bulk_store), ("graph", graph), ("order", order), ("head_ctas", head_ctas),
+                                    ("split_barrier", split_barrier)):
                     if value is not None:
                         _lib.check(lib.sstc_slab_set_option(h, name.encode(), int(value)))
                 torch.cuda.synchronize(dev)

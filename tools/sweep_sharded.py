@@ -19,11 +19,10 @@ dims = [512, 512, 512]
 n_loc = dims[0] * dims[1] * dims[2] // world
 x = torch.rand(n_loc, 2, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) - 0.5
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-KEYS = ("order", "chunks", "groups", "exchange_ctas", "head_ctas", "bulk_store")
+KEYS = ("order", "chunks", "groups", "exchange_ctas", "head_ctas", "bulk_store", "split_barrier")
 configs = [dict(zip(KEYS, v)) for v in
-           [(0, 4, 4, sms, 0, 0), (1, 2, 4, sms, 0, 0), (1, 2, 4, sms, 2 * sms, 0), (1, 2, 4, sms, sms, 0), (1, 2, 2, sms, 0, 0),
-            (1, 2, 8, sms, 0, 0), (1, 4, 4, sms, 0, 0), (1, 2, 4, 2 * sms, 0, 0), (1, 2, 4, sms, 0, 2), (1, 2, 4, sms, 2 * sms, 2),
-            (1, 4, 2, sms, 0, 0), (1, 8, 4, sms, 0, 0)]]
+           [(0, 4, 4, sms, 0, 0, 0), (0, 4, 4, sms, 0, 0, 1), (0, 1, 4, sms, 0, 0, 0), (0, 1, 4, sms, 0, 0, 1),
+            (0, 4, 4, sms, 0, 0, 0), (0, 4, 4, sms, 0, 0, 1), (0, 4, 4, sms, 0, 2, 0), (0, 4, 2, sms, 0, 0, 0)]]
 if len(sys.argv) > 1:
     configs = [dict(zip(KEYS, map(int, a.split(",")))) for a in sys.argv[1:]]
 ref, out = None, []
