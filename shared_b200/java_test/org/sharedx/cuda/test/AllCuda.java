@@ -59,7 +59,7 @@ public class AllCuda {
 
         Control.checkTrue(ArrayBase.opKernel.useRegisteredKernel() //
                 && ArrayBase.fftService.useRegisteredService() //
-                && ImageOps.ImKernel.useRegisteredKernel(), //
+                && ImageOps.imKernel.useRegisteredKernel(), //
                 "Could not link the CUDA providers");
 
         Tests.runTests("CUDA Provider Tests", //
