@@ -565,7 +565,7 @@ def e2e_single_gpu(shared_b200, lib, local, n, flops, steps):
     arrays = [(a, b) for (a, b, _, _) in pins]
     run(arrays, 2, 1)  # warm-up: plans, slots, device buffers
     single = run(arrays, 1, steps)
-    double = run(arrays, 2, max(1, steps // 2 + 1))
+    double = run(arrays, 2, max(4, steps + 2))  # per caller; the first upload and the last download have no partner
     check(arrays)
     for (_, _, p_in, p_out) in pins:
         lib.sstc_host_free(p_in)
@@ -579,7 +579,7 @@ def e2e_single_gpu(shared_b200, lib, local, n, flops, steps):
         pages.append((h_in, np.zeros(2 * n)))
     run(pages, 2, 1)  # warm-up: staging rings, copy threads
     p_single = run(pages, 1, max(2, steps // 2))
-    p_double = run(pages, 2, max(1, steps // 2))
+    p_double = run(pages, 2, max(3, steps // 2 + 1))
     check(pages)
     h2d = d2h = 16 * n
     res = {"value": flops / double / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -84,8 +84,10 @@ int sstc_fft_set_devices(int ndev, const int32_t *devices);
  *                  streams and pinned staging ring, so that one caller's D2H overlaps another's H2D);
  *   "copy_threads" threads that move pageable arrays through the pinned staging ring (default min(12, 3/4 of the cores));
  *   "chunk_mib"    staging / pipelining granularity (default 32);
- *   "pipeline"     0 = H2D, all passes, D2H strictly one after the other (for A/B measurements), 1 = default.
- * Environment: SSTC_HOST_SLOTS, SSTC_HOST_COPY_THREADS, SSTC_HOST_CHUNK_MIB, SSTC_HOST_PIPELINE. */
+ *   "pipeline"     0 = H2D, all passes, D2H strictly one after the other (for A/B measurements), 1 = default;
+ *   "link_tokens"  1 (default) = one call at a time per PCIe direction, so that concurrent callers fall into
+ *                  upload-while-the-other-downloads step instead of sharing a direction; 0 = no arbitration.
+ * Environment: SSTC_HOST_SLOTS, SSTC_HOST_COPY_THREADS, SSTC_HOST_CHUNK_MIB, SSTC_HOST_PIPELINE, SSTC_HOST_LINK_TOKENS. */
 int sstc_host_option(const char *name, int64_t value);
 /* Where the calling thread's last sstc_fft spent its time (milliseconds): out[0..11] = total, input phase (H2D + inner
  * axes), output phase (outermost axis + D2H), host copies pageable -> ring, ring -> pageable, host blocked on a ring

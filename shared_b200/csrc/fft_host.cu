@@ -362,6 +362,14 @@ bool host_is_pinned(const void *p) {
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+// One transform at a time per PCIe direction. Two calls that upload at the same time only halve each other's rate; what
+// overlaps usefully is one call's upload with another's download. A call therefore holds the link's IN token while its
+// input is on the bus and the OUT token while its output is, and the calls fall into step by themselves: caller A uploads,
+// then downloads while caller B uploads, and so on -- both copy engines busy, neither direction shared.
+static std::mutex g_link_in[16], g_link_out[16];
+static std::atomic<int64_t> g_opt_link_tokens{-1};
+static bool opt_link_tokens() { return option(g_opt_link_tokens, "SSTC_HOST_LINK_TOKENS", 1) != 0; }
+
 static const size_t kSmallCopy = 1u << 20;  // below this the driver's own pageable path costs less than a staging hand-off
 
 // One chunk host -> device on s_in. Returns the event recorded behind it.
@@ -496,7 +504,13 @@ static void run_pipelined(HostSlot &S, sstc_fft_plan_s &p, const double *in, dou
         S.need_ring(1, chunk);
     }
     const size_t nsteps = p.steps.size();
+    const bool tokens = opt_link_tokens();
+    std::unique_lock<std::mutex> link_in(g_link_in[S.device & 15], std::defer_lock), link_out(g_link_out[S.device & 15], std::defer_lock);
+    if (tokens) {
+        link_in.lock();
+    }
     const double t_begin = now_ms();
+    cudaEvent_t last_arrived = nullptr;
 
     // phase 1: the input arrives in chunks; every inner axis of the planes that are complete is transformed behind it
     const int64_t min_planes = std::max<int64_t>(1, (int64_t) ((chunk / 2) / std::max<size_t>(1, in_plane)));
@@ -505,6 +519,7 @@ static void run_pipelined(HostSlot &S, sstc_fft_plan_s &p, const double *in, dou
     for (size_t off = 0; off < in_bytes; k++) {
         const size_t len = std::min(chunk, in_bytes - off);
         cudaEvent_t arrived = h2d_chunk(S, d_in + off, reinterpret_cast<const char *>(in) + off, len, in_pinned, k);
+        last_arrived = arrived;
         off += len;
         const int64_t ready = off == in_bytes ? d0 : (int64_t) (off / in_plane);
         if (ready > planes_done && (ready - planes_done >= min_planes || off == in_bytes)) {
@@ -520,6 +535,14 @@ static void run_pipelined(HostSlot &S, sstc_fft_plan_s &p, const double *in, dou
         }
     }
 
+    if (tokens) {
+        // the input has left the bus: hand the upload direction on, then wait for the download direction
+        if (last_arrived) {
+            SSTC_CUDA(cudaEventSynchronize(last_arrived));
+        }
+        link_in.unlock();
+        link_out.lock();
+    }
     t_stats.phase1_ms = now_ms() - t_begin;
     t_stats.chunks_in = k;
     const double t_phase2 = now_ms();
@@ -697,6 +720,8 @@ int sstc_host_option(const char *name, int64_t value) {
             g_opt_pipeline.store(value);
         } else if (n == "chunk_mib") {
             g_opt_chunk_mib.store(value);
+        } else if (n == "link_tokens") {
+            g_opt_link_tokens.store(value);
         } else {
             throw std::runtime_error("Unknown option");
         }

@@ -81,6 +81,10 @@ struct FftPassArgs {
     int64_t ntiles;      // tiles in this launch (set by the launcher); the grid may be smaller
     int64_t grid_limit;  // 0 = one CTA per tile
     int reverse;         // process the tiles in descending order
+    // STRIDED hot path only: every thread of a tile also issues one prefetch.global.L2 for a row segment of the tile
+    // `prefetch_ahead` tiles further on (0 = off), so that the page walks and the DRAM reads of a tile with a huge row
+    // stride (the outermost pass: every row in its own 2 MiB page) are under way before its CTA starts.
+    int prefetch_ahead;
 };
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -247,7 +251,7 @@ struct Pow2Stages<L, C, STRIDED, L> {
 // One tile (C lines of length L) of one pass; `blk` is the tile number. EXT = false is the lean hot path
 // (natural layout); EXT = true adds explicit point strides, blocked addressing and the line scatter, which
 // cost registers the hot path cannot spare at 1024 resident threads per SM.
-template <int L, int C, bool STRIDED, bool EXT>
+template <int L, int C, bool STRIDED, bool EXT, bool PF = false>
 __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_t blk, double2 *sm) {
     using Tile = Pow2Tile<L, C, STRIDED>;
     constexpr int T = Tile::T;
@@ -320,6 +324,18 @@ __device__ __forceinline__ void fft_pow2_tile(const FftPassArgs &a, const int64_
 #pragma unroll
             for (int m = 0; m < 8; m++) {
                 v[m] = a.in[in_base + (int64_t) (t + m * T) * in_ks];
+            }
+            if (PF && !EXT && STRIDED) {
+                const int64_t fb = blk + a.prefetch_ahead;
+                if (fb < (int64_t) gridDim.x) {
+                    const int64_t tiles_per_plane = (a.inner + C - 1) / C;
+                    const int64_t fo = fb / tiles_per_plane, fi = (fb - fo * tiles_per_plane) * C;
+                    // thread tid -> row tid of the future tile (THREADS == L whenever C == 8)
+                    for (int r = tid; r < L; r += Tile::THREADS) {
+                        const double2 *p = a.in + fo * a.in_plane + (int64_t) r * a.inner + fi;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                    }
+                }
             }
             if (EXT && a.mul) {
 #pragma unroll
@@ -466,6 +482,15 @@ __global__ void __launch_bounds__(Pow2Tile<L, C, STRIDED>::THREADS, Pow2Tile<L, 
 fft_pow2_kernel(const FftPassArgs a) {
     extern __shared__ double2 sm[];
     fft_pow2_tile<L, C, STRIDED, false>(a, blockIdx.x, sm);
+}
+
+// The same with the L2 prefetch of a tile further on (FftPassArgs::prefetch_ahead); a separate instantiation because the
+// extra address arithmetic does not fit the hot path's 64 registers without spilling.
+template <int L, int C>
+__global__ void __launch_bounds__(Pow2Tile<L, C, true>::THREADS, Pow2Tile<L, C, true>::MIN_CTAS)
+fft_pow2_pf_kernel(const FftPassArgs a) {
+    extern __shared__ double2 sm[];
+    fft_pow2_tile<L, C, true, false, true>(a, blockIdx.x, sm);
 }
 
 // ---------------------------------------------------------------------------------------------------------

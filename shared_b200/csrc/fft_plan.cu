@@ -146,6 +146,16 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
     const bool ext = a.ksplit > 0 || a.in_ksplit > 0 || a.ls_group > 0 || a.grid_limit > 0 || a.reverse || a.mul ||
             a.crop_cols > 0 || (STRIDED && (a.in_kstride != a.inner || a.out_kstride != a.inner));
     if (!ext) {
+        if (STRIDED && L == 512 && a.prefetch_ahead > 0 && a.mode == MODE_C2C) {
+            static std::once_flag pf_once[16];
+            std::call_once(pf_once[dev & 15], [] {
+                SSTC_CUDA(cudaFuncSetAttribute(fft_pow2_pf_kernel<L, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        Pow2Tile<L, C, true>::SMEM_BYTES));
+            });
+            fft_pow2_pf_kernel<L, C><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
+            check_launch("fft_pow2_pf_kernel");
+            return;
+        }
         fft_pow2_kernel<L, C, STRIDED><<<(unsigned) grid, Tile::THREADS, Tile::SMEM_BYTES, stream>>>(a);
         check_launch("fft_pow2_kernel");
         return;
@@ -162,6 +172,8 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
 // Diagnostics (sstc_exp_set "tma_strided"): 0 = off; 1 = the 512-point strided passes move their tiles with TMA, one
 // tile per CTA turn, two CTAs per SM; 3 = persistent CTAs with three tile buffers (load / transform / store overlapped).
 static std::atomic<int64_t> g_tma_strided{0};
+// Diagnostics / tuning (sstc_exp_set "l2_prefetch"): prefetch distance in tiles for the strided hot path (0 = off).
+static std::atomic<int64_t> g_l2_prefetch{0};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -476,6 +488,7 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.ls_group = a.ls_nblk = a.ls_first = a.ls_block_lines = a.ls_plane_lines = a.ls_sub = a.ls_bulk = 0;
     a.ntiles = a.grid_limit = 0;
     a.reverse = reverse;
+    a.prefetch_ahead = (int) g_l2_prefetch.load();
     a.mul = fuse ? fuse->mul : nullptr;
     a.crop_cols = fuse ? fuse->crop_cols : 0;
     a.crop_nd = fuse ? fuse->crop_nd : 0;
@@ -1143,6 +1156,8 @@ int sstc_exp_set(const char *name, int64_t value) {
             g_exchange_smem_kb.store(value);
         } else if (name && std::string(name) == "tma_strided") {
             g_tma_strided.store(value);
+        } else if (name && std::string(name) == "l2_prefetch") {
+            g_l2_prefetch.store(value);
         } else {
             throw std::runtime_error("Unknown option");
         }

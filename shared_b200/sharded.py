@@ -312,8 +312,7 @@ class ShardedFft3d:
     def __init__(self, dims, devices):
         self.dims = tuple(int(d) for d in dims)
         self.devices = [int(d) for d in devices]
-        for d in self.devices:
-            _lib.init(d)
+        _lib.init(self.devices[0])  # sstc_init also names the device NEW threads are bound to: keep it the first one
         h = ctypes.c_void_p()
         _lib.check(_lib.lib().sstc_fft3d_sharded_create(ctypes.byref(h), _lib.i32_array(self.dims), len(self.devices),
                                                         _lib.i32_array(self.devices)))

@@ -52,6 +52,17 @@ for name, (outer, L, inner) in (("512^3 y pass (stride 8 KB)", (512, 512, 512)),
         ms_oop = ev(lambda: s.fft_axis(x.data_ptr(), y.data_ptr(), outer, L, inner, False, 1.0, st))
         ms_inp = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), outer, L, inner, False, 1.0, st))
         rec[label] = {"out_of_place_ms": ms_oop, "in_place_ms": ms_inp, "in_place_gbs": 32 * n / ms_inp / 1e6, "bit_identical": same}
+    tma(0)
+    for ahead in (74, 148, 296, 592, 1184, 2368):
+        _lib.check(lib.sstc_exp_set(b"l2_prefetch", ahead))
+        y.zero_()
+        s.fft_axis(x.data_ptr(), y.data_ptr(), outer, L, inner, False, 1.0, st)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(y, ref))
+        ms_inp = ev(lambda: s.fft_axis(y.data_ptr(), y.data_ptr(), outer, L, inner, False, 1.0, st))
+        rec["registers + L2 prefetch %d tiles ahead" % ahead] = {"in_place_ms": ms_inp, "in_place_gbs": 32 * n / ms_inp / 1e6,
+                                                               "bit_identical": same}
+    _lib.check(lib.sstc_exp_set(b"l2_prefetch", 0))
     out["cases"].append(rec)
 del x, y, ref
 torch.cuda.empty_cache()
