@@ -15,6 +15,8 @@
 // Summation order differs from the reference's (a tile's partial sums are combined tree-wise), which is within the
 // scans' floating-point bar (relative L2 <= 1e-12 log2 N) and exact whenever the partial sums are exactly representable
 // (integer-valued inputs), as the parity tests check.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -30,8 +32,7 @@ constexpr int kScanThreads = 256;   // 8 warps: warp w owns rows 8w..8w+7 of the
 // as all-ones words (a NaN no arithmetic produces: published NaNs are canonicalised), and an aligned 8-byte store is
 // atomic, so a reader needs one round trip per predecessor and no fences.
 struct ScanDesc {
-    double agg[kT];
-    double pre[kT];
+    double2 ap[kT];  // .x = agg, .y = pre: side by side, so that one 16-byte load reads both (each half is its own atomic word)
 };
 
 struct Scan2dArgs {
@@ -45,10 +46,8 @@ struct Scan2dArgs {
 
 constexpr unsigned long long kNotReady = ~0ULL;
 
-__device__ __forceinline__ unsigned long long ld_word(const double *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void ld_pair(const double2 *p, unsigned long long &agg, unsigned long long &pre) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(agg), "=l"(pre) : "l"(p) : "memory");
 }
 
 __device__ __forceinline__ void publish(double *p, double v) {
@@ -103,11 +102,11 @@ __device__ __forceinline__ double look_back(const ScanDesc *desc, int64_t pos, i
     int64_t p = pos - step;
     for (int k = 0; k < count; k++, p -= step) {
         for (;;) {
-            const unsigned long long pre = ld_word(&desc[p].pre[e]);
+            unsigned long long agg, pre;
+            ld_pair(&desc[p].ap[e], agg, pre);  // ONE round trip per predecessor
             if (pre != kNotReady) {
                 return carry + __longlong_as_double((long long) pre);
             }
-            const unsigned long long agg = ld_word(&desc[p].agg[e]);
             if (agg != kNotReady) {
                 carry += __longlong_as_double((long long) agg);
                 break;
@@ -189,7 +188,7 @@ __global__ void __launch_bounds__(kScanThreads) scan2d_kernel(const Scan2dArgs a
             tile[r][lane] = x0;
             tile[r][lane + 32] = x1;
             if (lane == 31) {
-                publish(&a.row_desc[pos].agg[r], x1);  // the row's sum over this tile
+                publish(&a.row_desc[pos].ap[r].x, x1);  // the row's sum over this tile
                 row_carry[r] = x1;                     // parked here until the carry is known
             }
         }
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(kScanThreads) scan2d_kernel(const Scan2dArgs a
         // ---- row carry: the sums of the tiles on the left ---------------------------------------------------------------
         if (tid < kT) {
             const double c = look_back(a.row_desc, pos, 1, tc, tid);
-            publish(&a.row_desc[pos].pre[tid], c + row_carry[tid]);
+            publish(&a.row_desc[pos].ap[tid].y, c + row_carry[tid]);
             row_carry[tid] = c;
         }
         __syncthreads();
@@ -216,9 +215,9 @@ __global__ void __launch_bounds__(kScanThreads) scan2d_kernel(const Scan2dArgs a
         // ---- column carry: S of the row just above the tile ---------------------------------------------------------------
         if (tid < kT) {
             const double own = col_part[0][tid] + col_part[1][tid] + col_part[2][tid] + col_part[3][tid];
-            publish(&a.col_desc[pos].agg[tid], own);
+            publish(&a.col_desc[pos].ap[tid].x, own);
             const double cc = look_back(a.col_desc, pos, a.tiles_c, tr, tid);
-            publish(&a.col_desc[pos].pre[tid], cc + own);
+            publish(&a.col_desc[pos].ap[tid].y, cc + own);
             col_carry[tid] = cc;
         }
         __syncthreads();
@@ -271,7 +270,8 @@ void scan2d_sum(const double *src, int64_t spitch, double *dst, int64_t dpitch, 
     a.ticket = reinterpret_cast<unsigned int *>(ws + 2 * desc_bytes);
     SSTC_CUDA(cudaMemsetAsync(ws, 0xFF, 2 * desc_bytes, stream));  // every descriptor word = "not ready"
     SSTC_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), stream));
-    const int grid = (int) std::min<int64_t>(nt, (int64_t) sm_count() * 6);
+    static const int per_sm = getenv("SSTC_SCAN2D_CTAS_PER_SM") ? std::max(1, atoi(getenv("SSTC_SCAN2D_CTAS_PER_SM"))) : 6;
+    const int grid = (int) std::min<int64_t>(nt, (int64_t) sm_count() * per_sm);
     if (border) {
         scan2d_kernel<true><<<grid, kScanThreads, 0, stream>>>(a);
     } else {

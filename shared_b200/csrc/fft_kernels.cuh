@@ -204,13 +204,30 @@ struct Pow2Stages {
     __device__ __forceinline__ static void run(double2 (&v)[8], int t, int c, double2 *sm,
             const double2 *__restrict__ tw) {
         if (NS > 1) {
+            if (R == 8 && NS >= 256) {
+                // The last stage of a long line: its 7 * NS table (57 KB at L = 4096) does not stay in L1 beside the tile
+                // traffic, and seven 16-byte twiddle loads per thread are nearly as much L2 -> SM traffic as the data.
+                // Three loads (w^k, w^2k, w^4k) and four complex products give the other four powers.
+                const int k = t & (NS - 1);
+                const double2 w1 = __ldg(&tw[k]), w2 = __ldg(&tw[NS + k]), w4 = __ldg(&tw[3 * NS + k]);
+                const double2 w3 = cmul(w1, w2), w5 = cmul(w4, w1), w6 = cmul(w4, w2);
+                const double2 w7 = cmul(w4, w3);
+                v[1] = cmul(v[1], w1);
+                v[2] = cmul(v[2], w2);
+                v[3] = cmul(v[3], w3);
+                v[4] = cmul(v[4], w4);
+                v[5] = cmul(v[5], w5);
+                v[6] = cmul(v[6], w6);
+                v[7] = cmul(v[7], w7);
+            } else {
 #pragma unroll
-            for (int b = 0; b < B; b++) {
-                int k = (t + b * T) & (NS - 1);
+                for (int b = 0; b < B; b++) {
+                    int k = (t + b * T) & (NS - 1);
 #pragma unroll
-                for (int r = 1; r < R; r++) {
-                    double2 w = __ldg(&tw[(r - 1) * NS + k]);  // w_{NS*R}^{r*k}; lanes read consecutive k
-                    v[b + r * B] = cmul(v[b + r * B], w);
+                    for (int r = 1; r < R; r++) {
+                        double2 w = __ldg(&tw[(r - 1) * NS + k]);  // w_{NS*R}^{r*k}; lanes read consecutive k
+                        v[b + r * B] = cmul(v[b + r * B], w);
+                    }
                 }
             }
         }

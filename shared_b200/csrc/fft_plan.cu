@@ -174,6 +174,10 @@ static void launch_pow2(const FftPassArgs &a, int64_t grid, cudaStream_t stream)
 static std::atomic<int64_t> g_tma_strided{0};
 // Diagnostics / tuning (sstc_exp_set "l2_prefetch"): prefetch distance in tiles for the strided hot path (0 = off).
 static std::atomic<int64_t> g_l2_prefetch{0};
+// Tuning (sstc_exp_set "long_strided_ctas"): strided passes whose tile fills an SM (L >= 2048: one 1024-thread CTA per SM)
+// run as a persistent grid of this many CTAs looping over the tiles instead of one CTA per tile, which takes the CTA
+// turnover (drain 1024 threads, schedule 1024 threads) out of every tile. 0 = one CTA per tile.
+static std::atomic<int64_t> g_long_strided_ctas{0};
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -489,6 +493,9 @@ static void launch_axis(const void *in, void *out, int64_t outer, int L, int64_t
     a.ntiles = a.grid_limit = 0;
     a.reverse = reverse;
     a.prefetch_ahead = (int) g_l2_prefetch.load();
+    if (L >= 2048 && inner > 1 && mode == MODE_C2C && g_long_strided_ctas.load() > 0) {
+        a.grid_limit = g_long_strided_ctas.load();
+    }
     a.mul = fuse ? fuse->mul : nullptr;
     a.crop_cols = fuse ? fuse->crop_cols : 0;
     a.crop_nd = fuse ? fuse->crop_nd : 0;
@@ -1158,6 +1165,8 @@ int sstc_exp_set(const char *name, int64_t value) {
             g_tma_strided.store(value);
         } else if (name && std::string(name) == "l2_prefetch") {
             g_l2_prefetch.store(value);
+        } else if (name && std::string(name) == "long_strided_ctas") {
+            g_long_strided_ctas.store(value);
         } else {
             throw std::runtime_error("Unknown option");
         }

@@ -56,6 +56,14 @@ res["c2c_columns_8x512_padded_in_interleaved_dense_out"] = ev(lambda: s.fft_axis
     wsp.data_ptr(), spec.data_ptr(), 8, 512, h, 512 * pad, pad, h, 8 * h, False, 1.0, st))
 res["c2c_columns_2x2048_padded_in_interleaved_dense_out"] = ev(lambda: s.fft_axis_strided(
     wsp.data_ptr(), spec.data_ptr(), 2, 2048, h, 2048 * pad, pad, h, 2 * h, False, 1.0, st))
+# persistent grid for the tile that fills an SM (one 1024-thread CTA): takes the CTA turnover out of every tile
+from shared_b200 import _lib
+for ctas in (148, 296, 444):
+    _lib.check(_lib.lib().sstc_exp_set(b"long_strided_ctas", ctas))
+    res["c2c_columns_4096_inner2049_inplace_persistent_%d" % ctas] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.data_ptr(), 1, n, h, False, 1.0, st))
+    res["c2c_columns_2048_inner4096_persistent_%d" % ctas] = ev(lambda: s.fft_axis(spec.data_ptr(), spec.data_ptr(), 1, 2048, 4096, False, 1.0, st))
+    res["rfft_total_persistent_%d" % ctas] = ev(lambda: p1.execute(r.data_ptr(), spec.data_ptr(), st))
+_lib.check(_lib.lib().sstc_exp_set(b"long_strided_ctas", 0))
 p2 = s.FftPlan(s.C2R, [n, n])
 res["rifft_total"] = ev(lambda: p2.execute(spec.data_ptr(), back.data_ptr(), st))
 res["bytes_c2c_pass_MB"] = 2 * 16 * n * h / 1e6
