@@ -597,6 +597,11 @@ static bool run_on_devices(int kind, int rank, const int32_t *dims, const double
     if (!sharded_shape(kind, rank, dims, ndev)) {
         return false;
     }
+    // Pageable arrays are bound by the host-side staging copies (44-75 GB/s for the whole box), not by the links: measured
+    // on 4 GPUs, 92-112 ms over 2-4 devices against 86-92 ms on one (profiles/r2_exp_devices_hint.json). They stay on one.
+    if (!host_is_pinned(in) || !host_is_pinned(out)) {
+        return false;
+    }
     std::vector<int32_t> key(g_devices);
     key.insert(key.end(), dims, dims + rank);
     auto it = g_sharded_plans.find(key);

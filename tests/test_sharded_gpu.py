@@ -102,22 +102,37 @@ def test_devices_hint_routes_the_provider_call_over_all_gpus():
     if p < 2:
         pytest.skip("needs at least two GPUs")
     p = 1 << int(math.log2(p))
+    import ctypes
+    from shared_b200 import _lib
     svc = s.CudaFftService(0)
     dims = [128, 128, 128]
     n = 128 ** 3
-    x = np.random.default_rng(77).uniform(-0.5, 0.5, 2 * n)
-    one = np.empty_like(x)
+
+    def pinned(nd):  # the multi-device route takes pinned arrays only (pageable ones are staging-bound and stay on one device)
+        p = ctypes.c_void_p()
+        _lib.check(_lib.lib().sstc_host_alloc(ctypes.byref(p), nd * 8))
+        return np.frombuffer((ctypes.c_double * nd).from_address(p.value), dtype=np.float64)
+
+    x = pinned(2 * n)
+    x[:] = np.random.default_rng(77).uniform(-0.5, 0.5, 2 * n)
+    one = pinned(2 * n)
     svc.fft(dims, x, one)
     try:
         svc.setHint("devices", ",".join(str(d) for d in range(p)))
         assert svc.getHint("devices") == ",".join(str(d) for d in range(p))
-        many = np.empty_like(x)
+        many = pinned(2 * n)
         svc.fft(dims, x, many)
+        from shared_b200 import _lib as _l
+        st = (ctypes.c_double * 12)()
+        _l.lib().sstc_host_last_stats(st, 12)
         want = oracle.fft(dims, x)
         assert np.linalg.norm(many - want) / np.linalg.norm(want) < 1e-12 * math.log2(n)
         assert np.linalg.norm(many - one) / np.linalg.norm(one) < 1e-13
-        back = np.empty_like(x)
+        back = pinned(2 * n)
         svc.ifft(dims, many, back)
+        pageable = np.empty(2 * n)
+        svc.fft(dims, np.array(x), pageable)  # pageable arrays: one device, the single-device bits
+        assert np.array_equal(pageable, one)
         assert np.linalg.norm(back - x) / np.linalg.norm(x) < 1e-12 * math.log2(n)
         # shapes the slab transform does not take stay on one device
         small = np.random.default_rng(78).uniform(-0.5, 0.5, 2 * 6 * 10 * 12)
@@ -129,6 +144,6 @@ def test_devices_hint_routes_the_provider_call_over_all_gpus():
             svc.setHint("devices", "0,99")
     finally:
         svc.setHint("devices", "")
-    again = np.empty_like(x)
+    again = pinned(2 * n)
     svc.fft(dims, x, again)
     assert np.array_equal(again, one)
