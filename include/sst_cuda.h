@@ -192,6 +192,11 @@ int sstc_slab_create(sstc_slab *slab, const int32_t *dims, int nranks, int rank,
         void *const *d_flags);
 int sstc_slab_forward(sstc_slab slab, const double *d_in, double **d_out, void *stream);
 int sstc_slab_inverse(sstc_slab slab, const double *d_in, double **d_out, void *stream);
+/* For a STREAM of independent transforms: issues the local y pass of a transform now, on its own stream, so that it runs
+ * beside the exchange of the transform in flight; the next sstc_slab_forward with the same d_in finishes it (exchange and
+ * x passes only). At most two transforms may be begun ahead; they are finished in the order they were begun, and no
+ * inverse may be issued in between. A caller that overlaps this way keeps d_in unchanged until the matching forward. */
+int sstc_slab_forward_begin(sstc_slab slab, const double *d_in, void *stream);
 /* Options: "groups" (pipeline groups of the exchange, default 4), "chunks" (the local pass in front of the exchange is
  * cut into this many pieces and the first group follows piece by piece; default 4 at 8 ranks, else 1), "exchange_ctas"
  * (grid cap of the exchange pass; default one CTA per SM, two at 2 ranks; 0 = uncapped), "bulk_store" (1: every

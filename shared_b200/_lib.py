@@ -66,6 +66,7 @@ SIGNATURES = {
                                                    ctypes.c_int, ctypes.c_double, ctypes.c_int64, ctypes.c_void_p]),
     "sstc_slab_create": (ctypes.c_int, [c_void_pp, c_i32_p, ctypes.c_int, ctypes.c_int, c_void_pp, c_void_pp, c_void_pp]),
     "sstc_slab_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
+    "sstc_slab_forward_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "sstc_slab_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_void_pp, ctypes.c_void_p]),
     "sstc_slab_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "sstc_slab_trace": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),

@@ -22,6 +22,7 @@
 
 #include <map>
 #include <algorithm>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -43,6 +44,17 @@ struct sstc_slab_s {
     int groups = 4, chunks = 1, exchange_ctas = 0, bulk = 0, use_graph = 1;
     int order = 0, head_ctas = 0;  // see issue_forward
     int split_barrier = 0;         // see barrier_after_exchange
+    // forward_begin (the local y pass of a LATER transform issued ahead, beside the exchange of the current one)
+    double *work_alt = nullptr;                 // second work buffer: begun transforms alternate between the two
+    cudaStream_t s_y = nullptr;
+    cudaEvent_t ev_begin_enter[2] = {nullptr, nullptr}, ev_y_done[2] = {nullptr, nullptr}, ev_step_done = nullptr;
+    bool have_step_done = false;
+    uint64_t begin_count = 0;
+    struct Pending {
+        const double *in;
+        int widx;
+    };
+    std::deque<Pending> pending;
     uint64_t step = 0;
     std::map<std::tuple<int, const void *, int>, cudaGraphExec_t> graphs;
     std::map<std::tuple<int, const void *, int>, int64_t> graph_kernels;
@@ -124,12 +136,14 @@ static cudaEvent_t barrier_after_exchange(sstc_slab_s &S) {
 //   order 1  chunk-major first, group-major last: E(c, all groups) as ONE launch per chunk for c < C-1, uncapped (nothing
 //            needs the SMs yet but the next chunk's y pass), then the last chunk group by group with the x passes beside
 //            it. The link starts after 1/C of the y pass and never waits for a small launch.
-static void issue_forward(sstc_slab_s &S, const double *x, int parity) {
+// x == nullptr: the y pass of this transform was issued ahead (sstc_slab_forward_begin) into `work_buf` and s_main has
+// already waited for it; the exchange then starts at full speed, group 0 included.
+static void issue_forward(sstc_slab_s &S, const double *x, int parity, double *work_buf) {
     const int P = S.nranks;
-    const int G = pick_divisor(S.groups, S.y_loc), C = pick_divisor(S.chunks, S.x_loc);
+    const int G = pick_divisor(S.groups, S.y_loc), C = x ? pick_divisor(S.chunks, S.x_loc) : 1;
     const int yg = S.y_loc / G, xc = S.x_loc / C;
     const int64_t cols = (int64_t) yg * S.d2, kstride = (int64_t) S.y_loc * S.d2, plane = (int64_t) S.d1 * S.d2;
-    char *work = reinterpret_cast<char *>(S.work);
+    char *work = reinterpret_cast<char *>(work_buf);
     void *base[8];
     for (int q = 0; q < P; q++) {
         base[q] = static_cast<char *>(S.recv[parity][q]) + (size_t) S.rank * S.block * 16;
@@ -144,8 +158,10 @@ static void issue_forward(sstc_slab_s &S, const double *x, int parity) {
     mark(S, S.s_main, "start");
     for (int c = 0; c < C; c++) {
         const size_t off = (size_t) c * xc * plane * 16;
-        fft_axis_pass(reinterpret_cast<const char *>(x) + off, work + off, xc, S.d1, S.d2, PASS_C2C, 0, 1.0, S.s_main);
-        y_done.push_back(record_on(S, S.s_main));
+        if (x) {
+            fft_axis_pass(reinterpret_cast<const char *>(x) + off, work + off, xc, S.d1, S.d2, PASS_C2C, 0, 1.0, S.s_main);
+        }
+        y_done.push_back(record_on(S, S.s_main));  // (pre-begun: the fork point of the side streams)
         mark(S, S.s_main, "y" + std::to_string(c) + " done");
     }
     const bool two_phase = S.order == 1 && C > 1;
@@ -185,7 +201,7 @@ static void issue_forward(sstc_slab_s &S, const double *x, int parity) {
             }
         } else {
             mark(S, S.s_z, "e" + std::to_string(g) + " begin");
-            fft_lines_scatter(S.work, base, P, S.x_loc, S.d1, S.d2, g * yg, yg, 0, 1.0, S.exchange_ctas, S.bulk, S.s_z);
+            fft_lines_scatter(work_buf, base, P, S.x_loc, S.d1, S.d2, g * yg, yg, 0, 1.0, S.exchange_ctas, S.bulk, S.s_z);
             mark(S, S.s_z, "e" + std::to_string(g) + " done");
         }
         cudaEvent_t arrived = barrier_after_exchange(S);
@@ -241,16 +257,31 @@ static void slab_run(sstc_slab_s &S, int dir, const double *in, double **out, cu
     cudaEvent_t enter = slab_event(S);
     SSTC_CUDA(cudaEventRecord(enter, user));
     SSTC_CUDA(cudaStreamWaitEvent(S.s_main, enter, 0));
-    const auto key = std::make_tuple(dir, (const void *) in, parity);
+    // a transform whose y pass was issued ahead?
+    double *work_buf = S.work;
+    bool begun = false;
+    int gdir = dir, gpar = parity;
+    if (dir == 0 && !S.pending.empty() && S.pending.front().in == in) {
+        const int widx = S.pending.front().widx;
+        S.pending.pop_front();
+        begun = true;
+        work_buf = widx ? S.work_alt : S.work;
+        SSTC_CUDA(cudaStreamWaitEvent(S.s_main, S.ev_y_done[widx], 0));
+        gdir = 2;
+        gpar = parity * 2 + widx;
+    } else if (!S.pending.empty()) {
+        throw std::runtime_error("a begun forward transform is pending: finish it with sstc_slab_forward on the same input first");
+    }
+    const auto key = std::make_tuple(gdir, (const void *) in, gpar);
     auto it = S.graphs.find(key);
-    if (it == S.graphs.end() && S.use_graph && !S.trace && S.seen[std::make_pair(dir, (const void *) in)] >= 2) {
+    if (it == S.graphs.end() && S.use_graph && !S.trace && S.seen[std::make_pair(gdir, (const void *) in)] >= 2) {
         // both parities have run eagerly with this input (attributes set, tables built): record this one
         cudaGraph_t graph = nullptr;
         const int64_t before = g_launch_count.load();
         SSTC_CUDA(cudaStreamBeginCapture(S.s_main, cudaStreamCaptureModeRelaxed));
         try {
             if (dir == 0) {
-                issue_forward(S, in, parity);
+                issue_forward(S, begun ? nullptr : in, parity, work_buf);
             } else {
                 issue_inverse(S, in, parity);
             }
@@ -276,17 +307,54 @@ static void slab_run(sstc_slab_s &S, int dir, const double *in, double **out, cu
         SSTC_CUDA(cudaGraphLaunch(it->second, S.s_main));
         count_launch((int) S.graph_kernels[key]);
     } else {
-        S.seen[std::make_pair(dir, (const void *) in)]++;
+        S.seen[std::make_pair(gdir, (const void *) in)]++;
         if (dir == 0) {
-            issue_forward(S, in, parity);
+            issue_forward(S, begun ? nullptr : in, parity, work_buf);
         } else {
             issue_inverse(S, in, parity);
         }
     }
+    if (!S.ev_step_done) {
+        SSTC_CUDA(cudaEventCreateWithFlags(&S.ev_step_done, cudaEventDisableTiming));
+    }
+    SSTC_CUDA(cudaEventRecord(S.ev_step_done, S.s_main));  // what a y pass issued ahead waits for before it reuses a work buffer
+    S.have_step_done = true;
     cudaEvent_t leave = slab_event(S);
     SSTC_CUDA(cudaEventRecord(leave, S.s_main));
     SSTC_CUDA(cudaStreamWaitEvent(user, leave, 0));
     *out = static_cast<double *>(S.recv[parity][S.rank]);
+}
+
+// The local y pass of a transform that sstc_slab_forward(in) will finish later, issued NOW on its own stream so that it
+// runs beside the exchange of the transform in flight: in a stream of independent transforms the head of every step (the
+// pass that must precede the first byte on the link) hides behind its predecessor. At most two transforms can be begun
+// ahead (two work buffers); they are finished in the order they were begun.
+static void slab_begin(sstc_slab_s &S, const double *in, cudaStream_t user) {
+    if (!in) {
+        throw std::runtime_error("Invalid arguments");
+    }
+    if (S.pending.size() >= 2) {
+        throw std::runtime_error("two forward transforms are already begun");
+    }
+    DeviceGuard guard(S.device);
+    if (!S.s_y) {
+        SSTC_CUDA(cudaStreamCreateWithFlags(&S.s_y, cudaStreamNonBlocking));
+        SSTC_CUDA(cudaMalloc(reinterpret_cast<void **>(&S.work_alt), (size_t) S.n_local * 16));
+        for (int i = 0; i < 2; i++) {
+            SSTC_CUDA(cudaEventCreateWithFlags(&S.ev_begin_enter[i], cudaEventDisableTiming));
+            SSTC_CUDA(cudaEventCreateWithFlags(&S.ev_y_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int widx = (int) (S.begin_count++ & 1);
+    SSTC_CUDA(cudaEventRecord(S.ev_begin_enter[widx], user));
+    SSTC_CUDA(cudaStreamWaitEvent(S.s_y, S.ev_begin_enter[widx], 0));
+    if (S.have_step_done) {
+        // this work buffer was last read two steps ago; the latest finished step is a (more than) sufficient fence
+        SSTC_CUDA(cudaStreamWaitEvent(S.s_y, S.ev_step_done, 0));
+    }
+    fft_axis_pass(in, widx ? S.work_alt : S.work, S.x_loc, S.d1, S.d2, PASS_C2C, 0, 1.0, S.s_y);
+    SSTC_CUDA(cudaEventRecord(S.ev_y_done[widx], S.s_y));
+    S.pending.push_back({in, widx});
 }
 
 static void slab_destroy(sstc_slab_s *S) {
@@ -296,10 +364,21 @@ static void slab_destroy(sstc_slab_s *S) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(S->device);
-    for (cudaStream_t s : {S->s_main, S->s_z, S->s_bar, S->s_x}) {
+    for (cudaStream_t s : {S->s_main, S->s_z, S->s_bar, S->s_x, S->s_y}) {
         if (s) {
             cudaStreamSynchronize(s);
         }
+    }
+    for (cudaEvent_t e : {S->ev_begin_enter[0], S->ev_begin_enter[1], S->ev_y_done[0], S->ev_y_done[1], S->ev_step_done}) {
+        if (e) {
+            cudaEventDestroy(e);
+        }
+    }
+    if (S->s_y) {
+        cudaStreamDestroy(S->s_y);
+    }
+    if (S->work_alt) {
+        cudaFree(S->work_alt);
     }
     for (auto &g : S->graphs) {
         cudaGraphExecDestroy(g.second);
@@ -485,6 +564,16 @@ int sstc_slab_forward(sstc_slab slab, const double *d_in, double **d_out, void *
             throw std::runtime_error("Invalid arguments");
         }
         slab_run(*slab, 0, d_in, d_out, as_stream(stream));
+    });
+}
+
+int sstc_slab_forward_begin(sstc_slab slab, const double *d_in, void *stream) {
+    return guarded([&] {
+        if (!slab) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        check_barrier_error();
+        slab_begin(*slab, d_in, as_stream(stream));
     });
 }
 

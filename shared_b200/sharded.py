@@ -213,6 +213,15 @@ class SlabFft3d:
                 return b.tensor
         raise RuntimeError("sstc_slab returned a pointer outside its receive buffers")
 
+    def forward_begin(self, x):
+        """Issues the local y pass of a LATER forward(x) now (sstc_slab_forward_begin): in a loop over independent
+        transforms, `forward_begin(next); out = forward(current)` hides every step's head behind its predecessor's
+        exchange. `x` must stay unchanged until the matching forward."""
+        if self._slab is None:
+            raise ValueError("forward_begin() is for the 'pipe' exchange")
+        stream = torch.cuda.current_stream(self.engine.device).cuda_stream
+        _lib.check(_lib.lib().sstc_slab_forward_begin(self._slab, ctypes.c_void_p(int(x.data_ptr())), ctypes.c_void_p(stream)))
+
     def capture(self, x):
         """Two eager steps with input buffer `x` (one per receive buffer): from the third call on, the C side replays
         the schedule from a CUDA graph (sstc_slab_forward records one per input pointer and buffer parity)."""

@@ -42,6 +42,22 @@ for dims in ([64, 64, 64], [128, 64, 32]) + (() if args.small else ([512, 512, 5
                 ok_all = False
                 if rank == 0:
                     print("dims", dims, "world", world, mode, "step", it, "differs from step 0 FAIL", flush=True)
+        if mode == "pipe":
+            # a stream of independent transforms with every y pass issued one step ahead (forward_begin): same bits
+            slab.forward_begin(mine)
+            for it in range(6):
+                slab.forward_begin(mine)
+                out = slab.forward(mine)
+                shards = [torch.empty_like(out) for _ in range(world)]
+                dist.all_gather(shards, out.contiguous())
+                if not torch.equal(gather_transposed(shards, dims).reshape(n, 2), first):
+                    ok_all = False
+                    if rank == 0:
+                        print("dims", dims, "world", world, "forward_begin step", it, "differs FAIL", flush=True)
+            out = slab.forward(mine)  # finishes the last begun transform
+            shards = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(shards, out.contiguous())
+            got = gather_transposed(shards, dims).reshape(n, 2)
         err = (torch.linalg.norm(got - ref) / torch.linalg.norm(ref)).item()
         exact = torch.equal(got, ref)
         back = slab.inverse(out.clone())

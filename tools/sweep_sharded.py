@@ -19,29 +19,42 @@ dims = [512, 512, 512]
 n_loc = dims[0] * dims[1] * dims[2] // world
 x = torch.rand(n_loc, 2, dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank)) - 0.5
 sms = torch.cuda.get_device_properties(dev).multi_processor_count
-KEYS = ("order", "chunks", "groups", "exchange_ctas", "head_ctas", "bulk_store", "split_barrier")
+KEYS = ("order", "chunks", "groups", "exchange_ctas", "head_ctas", "bulk_store", "split_barrier", "begin_ahead")
 configs = [dict(zip(KEYS, v)) for v in
-           [(0, 4, 4, sms, 0, 0, 0), (0, 4, 4, sms, 0, 0, 1), (0, 1, 4, sms, 0, 0, 0), (0, 1, 4, sms, 0, 0, 1),
-            (0, 4, 4, sms, 0, 0, 0), (0, 4, 4, sms, 0, 0, 1), (0, 4, 4, sms, 0, 2, 0), (0, 4, 2, sms, 0, 0, 0)]]
+           [(0, 4, 4, sms, 0, 0, 0, 0), (0, 4, 4, sms, 0, 0, 0, 1), (0, 4, 8, sms, 0, 0, 0, 1), (0, 4, 2, sms, 0, 0, 0, 1),
+            (0, 4, 4, 120, 0, 0, 0, 1), (0, 4, 4, 190, 0, 0, 0, 1), (0, 4, 4, sms, 0, 2, 0, 1), (0, 4, 4, sms, 0, 0, 1, 1),
+            (0, 4, 4, 2 * sms, 0, 2, 0, 1), (0, 4, 8, sms, 0, 0, 1, 1)]]
 if len(sys.argv) > 1:
     configs = [dict(zip(KEYS, map(int, a.split(",")))) for a in sys.argv[1:]]
 ref, out = None, []
 for cfg in configs:
+    ahead = cfg.pop("begin_ahead", 0)
     slab = SlabFft3d(dims, exchange="pipe", device=local, **cfg)
+    cfg["begin_ahead"] = ahead
     y = slab.forward(x).clone()
     if ref is None:
         ref = y
     same = bool(torch.equal(y, ref))
     slab.capture(x)
+    if ahead:
+        slab.forward_begin(x)
+
+    def step():
+        if ahead:
+            slab.forward_begin(x)
+        return slab.forward(x)
+
     for _ in range(10):
-        slab.forward(x)
+        step()
     torch.cuda.synchronize()
     dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(200):
-        slab.forward(x)
+        step()
     b.record()
+    if ahead:
+        slab.forward(x)  # finishes the last begun transform
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) / 200], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
