@@ -488,7 +488,7 @@ def run_ours(args):
             "metric": METRIC, "value": flops / (ms_step * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": base_config(world, {"schedule": schedule}),
+            "config": base_config(world), "schedule": schedule,
             "hbm_model_gbs": 3 * 32.0 * n / ms_step / 1e6,
             "gpu_launches": int(launches), "launches_per_step": launches_per_step,
             "e2e": e2e,
