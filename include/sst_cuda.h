@@ -89,6 +89,10 @@ int sstc_fft_set_devices(int ndev, const int32_t *devices);
  *                  upload-while-the-other-downloads step instead of sharing a direction; 0 = no arbitration.
  * Environment: SSTC_HOST_SLOTS, SSTC_HOST_COPY_THREADS, SSTC_HOST_CHUNK_MIB, SSTC_HOST_PIPELINE, SSTC_HOST_LINK_TOKENS. */
 int sstc_host_option(const char *name, int64_t value);
+/* The staging copy of the host tier on its own (tests, diagnostics; needs no device): `rows` rows of `width` bytes from a
+ * host buffer with pitch `spitch` into one with pitch `dpitch`, spread over the copy threads, non-temporal stores. */
+int sstc_exp_host_copy(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t rows);
+
 /* Where the calling thread's last sstc_fft spent its time (milliseconds): out[0..11] = total, input phase (H2D + inner
  * axes), output phase (outermost axis + D2H), host copies pageable -> ring, ring -> pageable, host blocked on a ring
  * buffer's DMA (in, out), pipelined?, in pinned?, out pinned?, input chunks, output groups. */

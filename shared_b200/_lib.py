@@ -37,6 +37,8 @@ SIGNATURES = {
     "sstc_fft": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_i32_p, ctypes.c_void_p, ctypes.c_int64,
                                 ctypes.c_void_p, ctypes.c_int64]),
     "sstc_fft_set_devices": (ctypes.c_int, [ctypes.c_int, c_i32_p]),
+    "sstc_exp_host_copy": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.c_int64]),
     "sstc_host_last_stats": (ctypes.c_int, [c_dbl_p, ctypes.c_int]),
     "sstc_host_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "sstc_fft_plan_create": (ctypes.c_int, [c_void_pp, ctypes.c_int, ctypes.c_int, c_i32_p]),

@@ -697,6 +697,22 @@ int sstc_fft(int kind, int rank, const int32_t *dims, const double *in, int64_t 
     });
 }
 
+// Diagnostics / tests (no device needed): the staging copy the host tier uses for pageable arrays -- `rows` rows of `width`
+// bytes between pitched host buffers, spread over the copy threads, non-temporal stores.
+int sstc_exp_host_copy(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width, int64_t rows) {
+    try {
+        clear_last_error();
+        if (!dst || !src || width < 0 || rows < 0 || dpitch < width || spitch < width) {
+            throw std::runtime_error("Invalid arguments");
+        }
+        host_copy_rows(dst, (size_t) dpitch, src, (size_t) spitch, (size_t) width, (size_t) rows);
+        return 0;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return 1;
+    }
+}
+
 int sstc_host_last_stats(double *out, int n) {
     return guarded([&] {
         if (!out || n < 0) {
