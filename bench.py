@@ -588,7 +588,8 @@ def e2e_single_gpu(shared_b200, lib, local, n, flops, steps):
     arrays = [(a, b) for (a, b, _, _) in pins]
     run(arrays, 2, 1)  # warm-up: plans, slots, device buffers
     single = run(arrays, 1, steps)
-    double = run(arrays, 2, max(4, steps + 2))  # per caller; the first upload and the last download have no partner
+    reps2 = max(12, 2 * steps)  # per caller: the first upload and the last download have no partner (38 ms of ramp)
+    double = run(arrays, 2, reps2)
     check(arrays)
     for (_, _, p_in, p_out) in pins:
         lib.sstc_host_free(p_in)
@@ -606,15 +607,37 @@ def e2e_single_gpu(shared_b200, lib, local, n, flops, steps):
     check(pages)
     h2d = d2h = 16 * n
     res = {"value": flops / double / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": double * 1e3, "steps": steps, "callers": 2, "host_memory": "pinned",
+           "ms_per_step": double * 1e3, "steps": steps, "callers": 2, "transforms_timed": 2 * reps2,
+           "host_memory": "pinned",
            "api": "CudaFftService.fft -> sstc_fft (host tier), two caller threads, each call synchronous",
            "single_caller": {"ms_per_step": single * 1e3, "value": flops / single / 1e9, "unit": "GFLOP/s",
                              "bound": "one transform cannot finish before H2D + D2H: every output depends on every input"},
            "pageable": {"two_callers_ms_per_step": p_double * 1e3, "two_callers_value": flops / p_double / 1e9,
                         "single_caller_ms_per_step": p_single * 1e3, "single_caller_value": flops / p_single / 1e9,
                         "unit": "GFLOP/s", "note": "plain numpy arrays = what GetPrimitiveArrayCritical hands the JNI glue; "
-                        "staged through the pinned ring by the copy threads"}}
+                        "staged through the pinned ring by the copy threads"},
+           "host": host_topology()}
     return res
+
+
+def host_topology():
+    """NUMA nodes of the host and of the visible GPUs (sysfs), so that a flattening e2e curve can be read against the box."""
+    import glob
+    import os
+    out = {"numa_nodes": len(glob.glob("/sys/devices/system/node/node[0-9]*")), "cpus": os.cpu_count()}
+    try:
+        out["cpus_allowed"] = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    nodes = {}
+    for d in glob.glob("/sys/bus/pci/devices/*"):
+        try:
+            if open(d + "/vendor").read().strip() == "0x10de" and open(d + "/class").read().startswith("0x0302"):
+                nodes[os.path.basename(d)] = int(open(d + "/numa_node").read())
+        except (OSError, ValueError):
+            pass
+    out["gpu_numa_node"] = nodes
+    return out
 
 
 def e2e_sharded(torch, dist, lib, slab, x, dev, n, n_local, flops, stream, steps):
@@ -646,17 +669,89 @@ def e2e_sharded(torch, dist, lib, slab, x, dev, n, n_local, flops, stream, steps
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    def d2h():
+        lib.sstc_d2h(p_out, ctypes.c_void_p(x.data_ptr()), 16 * n_local, s)
+
+    # A stream of independent transforms, the N > 1 twin of the two-caller leg at N = 1: the upload of transform i + 1 and
+    # the download of transform i share the link in both directions. Two input slabs; the results alternate between the
+    # slab context's two receive buffers, and a result must have left before the next call (include/sst_cuda.h, sstc_slab).
+    x2 = torch.empty_like(x)
+    xs = (x, x2)
+    h_out2, p_out2 = pinned_array(2 * n_local)
+    outs = (p_out, p_out2)
+    main = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    c_in, c_out = ctypes.c_void_p(s_in.cuda_stream), ctypes.c_void_p(s_out.cuda_stream)
+
+    def stream_of(reps):
+        up = [torch.cuda.Event(), torch.cuda.Event()]
+        used = [None, None]  # forward that last read xs[b]
+        down = None
+
+        def upload(i):
+            b = i % 2
+            if used[b] is not None:
+                s_in.wait_event(used[b])
+            lib.sstc_h2d(ctypes.c_void_p(xs[b].data_ptr()), p_in, 16 * n_local, c_in)
+            up[b].record(s_in)
+
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        upload(0)
+        for i in range(reps):
+            b = i % 2
+            main.wait_event(up[b])
+            if down is not None:
+                main.wait_event(down)  # the previous result has left its receive buffer
+            out = slab.forward(xs[b])
+            done = torch.cuda.Event()
+            done.record(main)
+            used[b] = done
+            if i + 1 < reps:
+                upload(i + 1)
+            s_out.wait_event(done)
+            lib.sstc_d2h(outs[b], ctypes.c_void_p(out.data_ptr()), 16 * n_local, c_out)
+            down = torch.cuda.Event()
+            down.record(s_out)
+        main.wait_stream(s_in)
+        main.wait_stream(s_out)
+
+    def timed_stream(reps):
+        stream_of(6)  # both input pointers reach their graphs (recorded on the third call with the same pointer)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        stream_of(reps)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     e2e_s = timed(e2e_step, steps)
     h2d_s = timed(h2d, steps)  # all ranks copying at once: what the host's PCIe fabric gives N links together
+    d2h_s = timed(d2h, steps)  # and what the host's memory takes from them
+    reps_stream = max(24, 4 * steps)  # the first upload and the last download have no partner
+    stream_s = timed_stream(reps_stream)
+    expect = 0.25 * n
+    got = (float(h_out[0]), float(h_out2[0]))
+    assert dist.get_rank() != 0 or all(abs(g - expect) < 1e-6 * n for g in got), (got, expect)
     world = dist.get_world_size()
     lib.sstc_host_free(p_in)
     lib.sstc_host_free(p_out)
-    return {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
-            "ms_per_step": e2e_s * 1e3, "steps": steps, "callers": 1, "host_memory": "pinned",
-            "api": "sstc_h2d + SlabFft3d.forward (sstc_slab_forward) + sstc_d2h per rank",
+    lib.sstc_host_free(p_out2)
+    return {"value": flops / stream_s / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
+            "ms_per_step": stream_s * 1e3, "steps": steps, "transforms_timed": reps_stream, "host_memory": "pinned",
+            "api": "per rank: sstc_h2d + SlabFft3d.forward (sstc_slab_forward) + sstc_d2h; a stream of independent transforms, "
+                   "the upload of the next one beside the download of the last one (two input slabs, two result buffers)",
+            "single_caller": {"ms_per_step": e2e_s * 1e3, "value": flops / e2e_s / 1e9, "unit": "GFLOP/s",
+                              "note": "one transform at a time: upload, transform, download, synchronize"},
             "h2d_alone": {"ms": h2d_s * 1e3, "gbs_per_gpu": 16 * n_local / h2d_s / 1e9,
                           "gbs_all_gpus": 16 * n / h2d_s / 1e9,
-                          "note": "all %d ranks copying their slab at the same time" % world}}
+                          "note": "all %d ranks copying their slab at the same time" % world},
+            "d2h_alone": {"ms": d2h_s * 1e3, "gbs_per_gpu": 16 * n_local / d2h_s / 1e9,
+                          "gbs_all_gpus": 16 * n / d2h_s / 1e9},
+            "host": host_topology()}
 
 
 def main():
