@@ -21,19 +21,11 @@
 #include <vector>
 
 #include "array_common.cuh"
+#include "scan2d_core.cuh"
 
 namespace sstc {
 
-constexpr int kT = 64;              // tile edge
 constexpr int kScanThreads = 256;   // 8 warps: warp w owns rows 8w..8w+7 of the tile for the row scan
-
-// A tile's descriptor, per direction: its own sums (`agg`, per row over its columns / per column of Y over its rows) and
-// its inclusive prefix (`pre` = agg + everything left of / above the tile). The value IS the flag: the arrays start out
-// as all-ones words (a NaN no arithmetic produces: published NaNs are canonicalised), and an aligned 8-byte store is
-// atomic, so a reader needs one round trip per predecessor and no fences.
-struct ScanDesc {
-    double2 ap[kT];  // .x = agg, .y = pre: side by side, so that one 16-byte load reads both (each half is its own atomic word)
-};
 
 struct Scan2dArgs {
     const double *src;
@@ -44,76 +36,20 @@ struct Scan2dArgs {
     unsigned int *ticket;
 };
 
-constexpr unsigned long long kNotReady = ~0ULL;
-
-__device__ __forceinline__ void ld_pair(const double2 *p, unsigned long long &agg, unsigned long long &pre) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(agg), "=l"(pre) : "l"(p) : "memory");
-}
-
-__device__ __forceinline__ void publish(double *p, double v) {
-    if (v != v) {
-        v = __longlong_as_double(0x7FF8000000000000LL);  // never the "not ready" pattern
+// the descriptor words as the kernel touches them (scan2d_core.cuh's memory policy)
+struct DeviceScanMem {
+    static __device__ __forceinline__ void load_pair(const ScanPair *p, unsigned long long &agg, unsigned long long &pre) {
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(agg), "=l"(pre) : "l"(p) : "memory");
     }
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((unsigned long long) __double_as_longlong(v)) : "memory");
-}
-
-// Ticket -> tile position along anti-diagonals (d = tr + tc, tr ascending within a diagonal), in closed form: the
-// diagonals grow by one tile up to min(R, C), stay at min(R, C) tiles up to max(R, C), then shrink.
-__device__ __forceinline__ void ticket_to_tile(unsigned int t, int R, int C, int &tr, int &tc) {
-    const long long m = R < C ? R : C, M = R < C ? C : R, total = (long long) R * C;
-    const long long head = m * (m + 1) / 2, body = (M - m) * m;
-    long long d, first;
-    if (t < head) {
-        d = (long long) ((sqrt(8.0 * (double) t + 1.0) - 1.0) * 0.5);
-        while (d * (d + 1) / 2 > t) {
-            d--;
-        }
-        while ((d + 1) * (d + 2) / 2 <= t) {
-            d++;
-        }
-        first = d * (d + 1) / 2;
-    } else if (t < head + body) {
-        d = m + (t - head) / m;
-        first = head + (d - m) * m;
-    } else {
-        const long long u = total - 1 - t;  // mirrored: counts from the last tile
-        long long e = (long long) ((sqrt(8.0 * (double) u + 1.0) - 1.0) * 0.5);
-        while (e * (e + 1) / 2 > u) {
-            e--;
-        }
-        while ((e + 1) * (e + 2) / 2 <= u) {
-            e++;
-        }
-        d = (long long) R + C - 2 - e;
-        first = total - (e + 1) * (e + 2) / 2;
+    static __device__ __forceinline__ void store(double *p, unsigned long long bits) {
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(bits) : "memory");
     }
-    const long long first_tr = d - (C - 1) > 0 ? d - (C - 1) : 0;
-    tr = (int) (first_tr + (t - first));
-    tc = (int) (d - tr);
-}
+};
 
-// Sum of the predecessors' contributions for element `e` of the carry vector. `pos` walks towards the origin with
-// stride `step` (1 for the tiles on the left, tiles_c for the tiles above); `count` predecessors exist. With the tiles
-// handed out along anti-diagonals only the few diagonals in flight lack a prefix, so the walk is short. (A variant
-// in which all 256 threads read four predecessors per round was measured and is SLOWER -- 0.35 against 0.30 ms at
-// 8192 x 8192: the walk is already short, the extra barriers are not free.)
+__device__ __forceinline__ void publish(double *p, double v) { publish<DeviceScanMem>(p, v); }
+
 __device__ __forceinline__ double look_back(const ScanDesc *desc, int64_t pos, int64_t step, int count, int e) {
-    double carry = 0.0;
-    int64_t p = pos - step;
-    for (int k = 0; k < count; k++, p -= step) {
-        for (;;) {
-            unsigned long long agg, pre;
-            ld_pair(&desc[p].ap[e], agg, pre);  // ONE round trip per predecessor
-            if (pre != kNotReady) {
-                return carry + __longlong_as_double((long long) pre);
-            }
-            if (agg != kNotReady) {
-                carry += __longlong_as_double((long long) agg);
-                break;
-            }
-        }
-    }
-    return carry;
+    return look_back<DeviceScanMem>(desc, pos, step, count, e);
 }
 
 // BORDER: the input is the destination with its interior replaced by the source shifted by (1, 1) (createIntegralImage).
