@@ -456,7 +456,9 @@ def run_ours(args):
 
     # ---- e2e: host arrays, H2D + kernels + D2H inside the timed region -------------------------------------------
     e2e_steps = max(2, min(K, 6))
-    if world == 1:
+    if args.no_e2e:
+        e2e = None  # schedule sweeps only: a line without e2e is not a bench line
+    elif world == 1:
         e2e = e2e_single_gpu(shared_b200, lib, local, n, flops, e2e_steps)
     else:
         e2e = e2e_sharded(torch, dist, lib, slab, x, dev, n, n_local, flops, stream, e2e_steps)
@@ -774,6 +776,7 @@ def main():
                          "local y pass issued one step ahead; 0 = one at a time only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extra", action="store_true", dest="no_extra", help="skip extra_configs")
+    ap.add_argument("--no-e2e", action="store_true", dest="no_e2e", help="skip the e2e leg (schedule sweeps only)")
     ap.add_argument("--extra", default=None, help="comma-separated subset of extra configs (c1,c1b,c2,c4)")
     ap.add_argument("--no-graph", action="store_true", dest="no_graph", help="issue the pipe schedule eagerly")
     args = ap.parse_args()
