@@ -67,7 +67,7 @@ class ClockSampler:
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, gpu_index):
         self.gpu_index, self.rows, self.proc, self.thread = gpu_index, [], None, None
@@ -108,8 +108,17 @@ class ClockSampler:
                               ("sw_power_cap", 7)):
                 if r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]),
-                "power_w_max": max(float(r[3]) for r in inside), "reasons": sorted(reasons), "samples": len(inside)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(inside[0][2]),
+               "power_w_max": max(float(r[3]) for r in inside), "reasons": sorted(reasons), "samples": len(inside)}
+        try:
+            out["power_limit_w"] = float(inside[0][8])  # the limit sw_power_cap refers to
+        except (IndexError, ValueError):
+            pass
+        if "sw_power_cap" in reasons:
+            out["note"] = ("sustained FP64 FFT passes draw the board's power limit; the cap lowers the SM clock after ~0.1 s of "
+                           "load (profiles/r2_power_cap_vs_steps.json): --steps 20 measures the burst figure, longer runs the "
+                           "sustained one")
+        return out
 
 
 # --------------------------------------------------------------------------------------------------------
