@@ -312,9 +312,15 @@ static HostSlot *acquire_slot() {
                 SSTC_CUDA(cudaStreamCreateWithFlags(&s->s_run, cudaStreamNonBlocking));
                 SSTC_CUDA(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
             } catch (...) {
+                for (cudaStream_t st : {s->s_in, s->s_run, s->s_out}) {
+                    if (st) {
+                        cudaStreamDestroy(st);
+                    }
+                }
+                delete s;
                 lock.lock();
                 g_slots_created[d]--;
-                delete s;
+                g_slots_cv.notify_one();  // a caller waiting for a slot may now try to create one itself
                 throw;
             }
             return s;
