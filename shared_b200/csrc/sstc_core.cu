@@ -72,11 +72,10 @@ Scratch::~Scratch() {
 // all ranks map (CUDA IPC). Rank r publishes `epoch` into slot r of every rank's array, then waits until its
 // own array shows `epoch` from everyone. Launched after the kernel whose peer stores it fences, on the same
 // stream, so those stores are complete before the flag is written. One kernel per rank, each on its own GPU,
-// so the waiting ranks are always co-resident. A bounded spin (~4 s) turns a missing peer into stale data the
-// parity checks catch rather than a hung device.
-// sound or loud: a rank that gives up waiting records (epoch, missing rank) in a host-mapped word that every later
-// entry point of the library checks (check_barrier_error), so the transform whose barrier failed -- or at the latest
-// the next call -- raises instead of returning a slab that peers were still writing.
+// so the waiting ranks are always co-resident. The spin is bounded (~4 s) so that a missing peer cannot hang the
+// device, and the barrier is sound or loud: a rank that gives up waiting records (epoch, missing rank) in a host-mapped
+// word that every later entry point of the library checks (check_barrier_error), so the transform whose barrier failed
+// -- or at the latest the next call -- raises instead of returning a slab that peers were still writing.
 static unsigned long long *g_barrier_err_host = nullptr, *g_barrier_err_dev[16] = {nullptr};
 static std::mutex g_barrier_err_mutex;
 
