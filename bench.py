@@ -22,14 +22,16 @@ Keys beyond the base contract:
                 reports that latency. `value` is the throughput of TWO caller threads, each making the same
                 synchronous call (the SPI is thread-safe; the host tier gives every call its own slot), so that one
                 transform's D2H overlaps the other's H2D on the full-duplex link. `pageable` repeats both with plain
-                (unpinned) arrays, which is what a JVM heap array is. The reference arm uses the same two-caller client.
+                (unpinned) arrays, which is what a JVM heap array is. The reference arm is the same kind of client with one
+                caller thread per host core (the reference's FFT is single-threaded; callers are what can use the cores).
   parity        (N > 1) the step that is timed -- the recorded CUDA-graph replay -- checked outside the timed region
                 against the 1-GPU plan on the gathered input, plus the forward -> inverse round trip
   extra_configs BASELINE.json's other configs (C1, the reference's own benchmark loop, C2, C4; C5 at N = 8), each with
                 its own clocks, roofline, parity and cpu_baseline (bench_extra.py)
 
 `--impl reference` times the reference's own CPU algorithm (the oracle; there is no JVM or FFTW in the image)
-on a bounded sample per step, with the same two-caller client, and prints the same line with "impl": "reference".
+on a bounded sample per step, from one caller thread per host core (all the host threads the single-threaded reference
+can use), and prints the same line with "impl": "reference".
 """
 import argparse
 import ctypes
@@ -142,7 +144,8 @@ def base_config(n_gpus, extra=None):
     cfg = {"workload": "ComplexArray 512x512x512 complex128 3-D fft (forward)", "dims": list(DIMS),
            "parallelism": "1 GPU" if n_gpus == 1 else "slab x%d over d0, exchange over NVLink" % n_gpus,
            "l2": "inputs larger than L2 (2 GiB in + 2 GiB out vs 126 MB), no flush needed",
-           "client": "device-resident steps for `value`; two caller threads making synchronous provider calls for `e2e`"}
+           "client": "device-resident steps for `value`; caller threads making synchronous provider calls for `e2e` (ours: two, "
+                     "the PCIe link is full then; reference arm: one per host core)"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -186,29 +189,42 @@ def cpu_baseline(sample=(256, 256, 256)):
                       (sample + ((DIMS[0] * DIMS[1] * DIMS[2]) // n,))}
 
 
-REFERENCE_CALLERS = 2  # the same client as our e2e leg: two caller threads, each making synchronous provider calls
+def reference_callers():
+    """The reference's FFT is single-threaded, and its SPI may be called from any thread (Threading): the
+    arm that uses "all the host threads it can" is one caller thread per host core, each making synchronous calls on its
+    own arrays -- the same kind of client as our e2e leg, which stops at two callers only because the PCIe link is full
+    then. Bounded by memory (about 1 GiB per 256^3 caller) and by SSTC_REFERENCE_CALLERS."""
+    env = os.environ.get("SSTC_REFERENCE_CALLERS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    return max(1, min(cores, 32))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # 256^3 costs ~2.6 s per step on this pool's hosts (25 steps ~ 1 min); 512^3 would be ~25 s per step and 8 GiB per
-    # caller, so the step is a 1/8 sample of the workload -- GFLOP/s normalises the size (and the smaller cube fits the
-    # CPU's caches better, so the sample flatters the reference if anything)
+    # 256^3 costs ~2.6 s per transform on this pool's hosts; 512^3 would be ~25 s and 8 GiB per caller, so the step is a
+    # 1/8 sample of the workload -- GFLOP/s normalises the size (and the smaller cube fits the CPU's caches better, so the
+    # sample flatters the reference if anything)
     sample = (256, 256, 256)
     import numpy as np
     import oracle
     n = sample[0] * sample[1] * sample[2]
+    callers = reference_callers()
     rng = np.random.default_rng(SEED)
-    xs = [rng.uniform(-0.5, 0.5, 2 * n) for _ in range(REFERENCE_CALLERS)]
+    xs = [rng.uniform(-0.5, 0.5, 2 * n) for _ in range(callers)]
 
     def caller(x, steps):
         for _ in range(steps):
             oracle.fft(list(sample), x)
 
-    def run(steps):
-        th = [threading.Thread(target=caller, args=(x, steps)) for x in xs]
+    def run(steps, k):
+        th = [threading.Thread(target=caller, args=(x, steps)) for x in xs[:k]]
         t0 = time.perf_counter()
         for t in th:
             t.start()
@@ -217,28 +233,32 @@ def run_reference(args):
         return time.perf_counter() - t0
 
     # K steps in total, shared by the callers (rounded up to a whole number per caller)
-    per_caller = max(1, -(-args.steps // REFERENCE_CALLERS))
+    per_caller = max(1, -(-args.steps // callers))
     if args.warmup:
-        run(max(1, -(-args.warmup // REFERENCE_CALLERS)))
-    wall = run(per_caller)
-    transforms = per_caller * REFERENCE_CALLERS
+        run(max(1, -(-args.warmup // callers)), callers)
+    wall = run(per_caller, callers)
+    transforms = per_caller * callers
     secs = wall / transforms
     value = fft_flops(n) / secs / 1e9
-    single = cpu_fft_seconds(sample, 1)
+    single = run(1, 1)
+    two = run(1, min(2, callers)) / min(2, callers)
     desc = ("forward c2c %dx%dx%d per step (1/8 of the 512^3 points), oracle/fftops_oracle.c (C restatement of the "
-            "reference's FftOps.java; no JVM/FFTW in the image); %d caller threads, one single-threaded transform each "
-            "-- the reference has no threaded FFT" % (sample + (REFERENCE_CALLERS,)))
+            "reference's FftOps.java; no JVM/FFTW in the image); %d caller threads (one per host core), one single-threaded "
+            "transform each -- the reference has no threaded FFT" % (sample + (callers,)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": base_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": REFERENCE_CALLERS, "kind": "port", "sample": desc,
+        "config": base_config(args.gpus), "transforms_timed": transforms,
+        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": callers, "kind": "port", "sample": desc,
                          "host_cores": os.cpu_count(), "cpu_model": cpu_model(),
                          "single_caller": {"value": fft_flops(n) / single / 1e9, "unit": "GFLOP/s", "cores": 1,
-                                           "ms_per_step": single * 1e3}},
+                                           "ms_per_step": single * 1e3},
+                         "two_callers": {"value": fft_flops(n) / two / 1e9, "unit": "GFLOP/s", "cores": min(2, callers),
+                                         "ms_per_step": two * 1e3,
+                                         "note": "the client our e2e leg uses (its link is full with two)"}},
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "callers": REFERENCE_CALLERS},
+                "callers": callers},
     }))
 
 
