@@ -15,9 +15,12 @@
  */
 package org.sharedx.cuda;
 
+import java.io.Closeable;
+
 import org.shared.array.ComplexArray;
 
-public class CudaComplexArray implements AutoCloseable {
+// java.io.Closeable, not AutoCloseable: the reference builds at source level 1.6 (build.xml:8-9)
+public class CudaComplexArray implements Closeable {
 
     final int[] dims;
     final int length; // doubles
@@ -30,15 +33,20 @@ public class CudaComplexArray implements AutoCloseable {
             throw new IllegalArgumentException("Invalid dimensions");
         }
 
-        int n = 1;
+        long n = 1;
 
         for (int d : dims) {
-            n = Math.multiplyExact(n, d);
+
+            n *= d;
+
+            if (d < 0 || n > Integer.MAX_VALUE) {
+                throw new IllegalArgumentException("Invalid dimensions");
+            }
         }
 
         this.dims = dims.clone();
-        this.length = n;
-        this.devicePointer = allocate(n);
+        this.length = (int) n;
+        this.devicePointer = allocate(this.length);
     }
 
     /** Uploads a host array (one H2D copy). */
